@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py -- pairwise window comparisons/sec of the smafa query hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--kernel auto|popc|mma] [--mode a|b]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference's CPU algorithm on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: every query of the
+batch against every db window, max-divergence filter and best-hit selection included, producing
+the final hit rows.  Workload at N=1 = BASELINE.json configs[1]: 100k queries x 1M windows, 60 nt,
+--max-divergence 5 (Mode A).  At N>1 the db is row-sharded with a fixed 1M-window shard per GPU
+(weak scaling; N=8 is the 8M-window analogue of configs[2]) and the per-shard candidates are merged
+with an NCCL all-gather every step.
+
+`value`     : comparisons/s with queries and db resident in HBM (smafa_query_dev + merge).
+`e2e`       : the same through the host-facing call (pinned host queries in, host hit rows out;
+              H2D and D2H inside the timed region).
+`roofline`  : for the scan kernel, from CUDA events around it (smafa_stats.scan_ms).
+`cpu_baseline`: the oracle (a port of the reference's algorithm; the Rust reference cannot be built
+              in this image) timed on the host cores on a bounded query sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L = 60
+Q_DEFAULT = 100_000
+D_PER_GPU = 1_000_000
+MAX_DIVERGENCE = 5
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "mma"])
+    ap.add_argument("--mode", default="a", choices=["a", "b"], help="a: best hit + ties; b: --max-num-hits 10")
+    ap.add_argument("--queries", type=int, default=Q_DEFAULT)
+    ap.add_argument("--db-per-gpu", type=int, default=D_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_name(a, n):
+    k = "" if a.mode == "a" else " --max-num-hits 10"
+    return (f"synthetic {L}-nt SingleM windows: {a.queries} queries x {a.db_per_gpu * n} db "
+            f"({a.db_per_gpu}/GPU row shard), --max-divergence {MAX_DIVERGENCE}{k}")
+
+
+def make_inputs(a, rank, n):
+    from smafa_b200 import synth
+    # every rank derives its own shard from a rank-specific seed; queries come from shard 0's
+    # generator state so they are identical on every rank
+    db0 = synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB)
+    q_sym = synth.make_queries(db0, a.queries, seed=synth.SEED_QUERY)
+    shard = db0 if rank == 0 else synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB + 7919 * rank)
+    return synth.pack_symbols(shard), synth.pack_symbols(q_sym)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_baseline(db, q, seconds, mode_k):
+    """Times the oracle's query (all host threads) on a bounded prefix of the same queries."""
+    from oracle import c_oracle
+    c_oracle.build()
+    threads = os.cpu_count() or 1
+    D = db.shape[0]
+    probe = min(q.shape[0], 4 * threads)
+    t0 = time.perf_counter()
+    c_oracle.query(db, L, q[:probe], L, MAX_DIVERGENCE, mode_k, None, threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(q.shape[0], max(probe, probe * seconds / dt)))
+    n = max(threads, n // threads * threads)
+    t0 = time.perf_counter()
+    hits = c_oracle.query(db, L, q[:n], L, MAX_DIVERGENCE, mode_k, None, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n * D / dt, "unit": "comparisons/s", "cores": threads, "kind": "port",
+            "sample": f"first {n} of {q.shape[0]} queries x full {D}-window db, {dt:.1f} s, "
+                      f"-O3 -march=native, queries split statically over {threads} threads "
+                      f"(the reference itself is single-threaded)",
+            "seconds": dt, "rows": int(hits.shape[0])}, hits, n
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks):
+    """Roofline of the dominant (scan) kernel.  This path is compute-bound: operands
+    are reused Q x D times, compulsory HBM traffic is a few hundred MB per step."""
+    secs = scan_ms / 1e3
+    if kernel_used == 2:
+        ops = 2 * 5 * L  # int8 ops per comparison: one-hot(query) . one-hot(db)^T over 5 symbols x L
+        achieved = pairs_per_launch * ops / secs / 1e12
+        peak = 2.0 * peaks["bf16_tflops_sustained"]  # dense int8 = 2x bf16 on B200 (nominal 4.5 vs 2.25 PF)
+        return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": f"2 x {peaks_kind} bf16_tflops_sustained (int8 dense rate = 2 x bf16)",
+                "ops_per_comparison": ops}
+    # POPC formulation: the binding unit is the POPC pipe.  Reference layout = 10 x (XOR32+POPC32)
+    # per comparison (5 u64 words, src/lib.rs:85).  The bit-plane packing needs 2 (1 with early exit).
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    popc_peak = 148 * 16 * sm_mhz * 1e6 / 1e12  # 16 POPC lanes/clk/SM
+    achieved = pairs_per_launch * 10 / secs / 1e12
+    return {"bound": "alu", "achieved": achieved, "peak": popc_peak, "unit": "TPOPC/s (reference-layout popcounts)",
+            "frac": achieved / popc_peak, "traffic": None,
+            "peak_source": f"148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (sampled SM clock); the bit-plane packing "
+                           "issues 1-2 POPC per comparison instead of 10, so frac can exceed 1",
+            "ops_per_comparison": 10}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    db, q = make_inputs(a, 0, 1)
+    mode_k = None if a.mode == "a" else 10
+    times, cb = [], None
+    per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(1, a.steps + a.warmup)))
+    for i in range(a.warmup + a.steps):
+        cb, _, n = cpu_baseline(db, q, per_step, mode_k)
+        if i >= a.warmup:
+            times.append((cb["seconds"], n))
+    pairs = sum(n for _, n in times) * db.shape[0]
+    secs = sum(t for t, _ in times)
+    value = pairs / secs
+    cb["value"] = value
+    print(json.dumps({
+        "impl": "reference", "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / max(1, len(times)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64-popcount",
+        "data": "synthetic", "config": {"workload": workload_name(a, 1), "sampled": cb["sample"]},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": value, "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    import smafa_b200
+    from smafa_b200.dist import ShardedSearcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    db, q = make_inputs(a, rank, world)
+    ctx = smafa_b200.Context(local_rank, a.kernel)
+    searcher = ShardedSearcher(ctx, db, L, world_size=world, rank=rank, presharded=True)
+    mode_k = None if a.mode == "a" else 10
+    q_pinned = torch.from_numpy(q.view(np.int64)).pin_memory()
+    q_dev = q_pinned.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    pairs_per_step = a.queries * a.db_per_gpu * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing (value) ----
+    for _ in range(a.warmup):
+        rows = searcher.query_dev(q_dev, MAX_DIVERGENCE, mode_k)
+    n_rows = rows.shape[0]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    scan_ms, launches = 0.0, 0
+    t_wall = time.perf_counter()
+    for i in range(a.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        rows = searcher.query_dev(q_dev, MAX_DIVERGENCE, mode_k)
+        ev[i][1].record()
+        scan_ms += searcher.last_stats["scan_ms"]
+        launches += searcher.last_launches
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = pairs_per_step * a.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host-facing call ----
+    for _ in range(2):
+        host_rows = searcher.query_host(q_pinned, MAX_DIVERGENCE, mode_k)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        host_rows = searcher.query_host(q_pinned, MAX_DIVERGENCE, mode_k)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * a.steps / float(te.item())
+    assert host_rows.shape[0] == n_rows
+
+    if rank == 0:
+        peaks, peaks_kind = load_peaks()
+        st = searcher.last_stats
+        roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks)
+        out = {
+            "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s8" if st["kernel_used"] == 2 else "u32-popcount", "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "kernel": {1: "popc", 2: "mma", 0: "generic"}[st["kernel_used"]],
+                       "l2": "flushed between timed steps (256 MiB write)", "hit_rows": int(n_rows),
+                       "candidates_per_step": int(st["candidates"]), "parallelism": f"db-row-shard x{world}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "comparisons/s",
+                    "h2d_bytes_per_step": int(q.nbytes) * world, "d2h_bytes_per_step": int(host_rows.nbytes)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "scan_ms_per_step": scan_ms / a.steps, "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            cb, cpu_hits, n = cpu_baseline(db, q, a.cpu_seconds, mode_k)
+            got = host_rows[host_rows[:, 0] < n]
+            cb["matches_gpu_rows"] = bool(got.shape == cpu_hits.shape and (got == cpu_hits).all())
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    searcher.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+/*
+ * smafa_b200.h -- C ABI of libsmafa_b200.so, the B200 (sm_100a) drop-in for the query/cluster
+ * hot path of wwood/smafa v0.8.0.
+ *
+ * The reference has no FFI of its own: its hot path is the private method
+ * WindowSet::get_distances (src/lib.rs:71-89) plus the selection code inlined in query()
+ * (src/lib.rs:224-317) and cluster() (src/cluster.rs:45-74).  Each entry point below names the
+ * reference code it replaces; INTEGRATION.md shows the Rust `extern "C"` block and the
+ * call-site edits a maintainer would make.
+ *
+ * Conventions
+ *  - Encoded windows use the reference's bit layout (src/lib.rs:29-52): ceil(L/12) u64 words
+ *    per window, 5-bit one-hot code of symbol p at bit 5*(p%12) of word p/12.
+ *  - "None" for the Option<u32> parameters of smafa::query is passed as -1.
+ *  - All pointers are plain host pointers unless the name ends in _dev (then they are CUDA
+ *    device pointers on the context's device and `stream` is a cudaStream_t passed as void*).
+ *  - Input buffers are borrowed for the duration of the call.  Arrays returned through
+ *    smafa_hit** are owned by the library until smafa_free().
+ *  - Return value: SMAFA_OK (0) or a negative smafa_status.  No C++ exception crosses the ABI.
+ *    smafa_last_error() gives a message; for the three statuses that model reference panics
+ *    it is the reference's panic text.
+ *  - A context is single-owner, not re-entrant (the reference is single-threaded).  One context
+ *    drives one GPU; multi-GPU runs use one process per GPU (see smafa_b200/dist.py).
+ *  - There is no CPU fallback: without a usable sm_100 device every compute entry point
+ *    returns SMAFA_E_CUDA.
+ */
+#ifndef SMAFA_B200_H
+#define SMAFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMAFA_B200_ABI_VERSION 1
+
+typedef enum smafa_status {
+  SMAFA_OK = 0,
+  SMAFA_E_LENGTH_MISMATCH = -1, /* src/lib.rs:72-79 panic */
+  SMAFA_E_EMPTY_DB = -2,        /* src/lib.rs:254,298 Option::unwrap() on an empty db */
+  SMAFA_E_BAD_K = -3,           /* src/lib.rs:255 max_num_hits == 0 underflow */
+  SMAFA_E_LIMIT_NEEDS_K = -4,   /* src/lib.rs:301-303 limit_per_sequence without max_num_hits>1 */
+  SMAFA_E_CUDA = -10,
+  SMAFA_E_OOM = -11,
+  SMAFA_E_INVALID = -12,     /* bad argument (null pointer, L == 0 with D > 0, ...) */
+  SMAFA_E_UNSUPPORTED = -13, /* L > 4095 or D >= 2^32 */
+  SMAFA_E_IO = -20,          /* host file API: Err(..) in the reference (exit code 1) */
+  SMAFA_E_PANIC = -21        /* host file API: any other reference panic (exit code 101) */
+} smafa_status;
+
+/* Scan kernel formulations (north_star): both are kept, `AUTO` picks the measured default. */
+typedef enum smafa_kernel {
+  SMAFA_KERNEL_AUTO = 0,
+  SMAFA_KERNEL_POPC = 1, /* CUDA-core XOR/OR + POPC over the bit-plane re-packing */
+  SMAFA_KERNEL_MMA = 2   /* tcgen05 int8 MMA over one-hot operands, TMEM-drain epilogue */
+} smafa_kernel;
+
+typedef struct smafa_ctx smafa_ctx;
+typedef struct smafa_db smafa_db;
+
+/* One output row of `smafa query`: the first three TSV columns (src/lib.rs:292,310). */
+typedef struct smafa_hit {
+  uint32_t query;    /* 0-based query number */
+  uint32_t subject;  /* db window index (global: includes the shard's subject_offset) */
+  uint32_t distance; /* number of differing positions */
+} smafa_hit;
+
+/* Per-call statistics (optional out-parameter, may be NULL). */
+typedef struct smafa_stats {
+  uint64_t pairs;          /* Q x D comparisons covered */
+  uint64_t candidates;     /* rows the scan emitted before the final cutoff */
+  uint64_t kernel_launches;/* kernels launched by this call */
+  uint32_t retries;        /* candidate-buffer overflows that forced a smaller query batch */
+  uint32_t kernel_used;    /* smafa_kernel actually run */
+  float scan_ms;           /* device time of the scan kernels (CUDA events) */
+  float total_ms;          /* device time of the whole call */
+} smafa_stats;
+
+int smafa_abi_version(void);
+const char *smafa_status_name(int status);
+
+/* ---- context ------------------------------------------------------------------------- */
+int smafa_ctx_create(smafa_ctx **ctx, int device, int kernel /* smafa_kernel */);
+void smafa_ctx_destroy(smafa_ctx *ctx);
+/* Message for the last failure on this context (or the last failure of ctx-less calls when
+ * ctx == NULL).  Never NULL. */
+const char *smafa_last_error(const smafa_ctx *ctx);
+int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel);
+/* Candidate-buffer capacity in rows (testing hook for the overflow/retry path; 0 = default). */
+int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows);
+
+/* ---- db: replaces the in-memory WindowSet built by query() (src/lib.rs:208-218) ---------
+ * Re-packs D windows of length L into the GPU-resident matrices (bit planes for the POPC
+ * kernel, one-hot int8 tiles for the MMA kernel, reference words for exact verification and
+ * output).  subject_offset is added to every reported subject index (row-sharding across
+ * GPUs: SURVEY.md 8e).  D == 0 is allowed (queries then fail with SMAFA_E_EMPTY_DB, like
+ * the reference). */
+int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)] */, uint64_t D,
+                    uint32_t L, uint64_t subject_offset, smafa_db **db);
+/* Appends rows (used by cluster: the centroid set grows, src/cluster.rs:69-74). */
+int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n);
+uint64_t smafa_db_size(const smafa_db *db);
+uint32_t smafa_db_window_len(const smafa_db *db);
+void smafa_db_free(smafa_db *db);
+
+/* ---- get_distances (src/lib.rs:71-89), for parity/debug: out[q*D + i] ------------------ */
+int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q,
+                    uint32_t q_len, uint16_t *out /* [Q][D] */);
+
+/* ---- query: get_distances + selection (src/lib.rs:238-314) -----------------------------
+ * max_divergence / max_num_hits: -1 == None.  None or 1 => "Mode A" (all ties at the
+ * minimum, ascending subject); any other k => "Mode B" (everything <= the k-th smallest
+ * distance, ties included, in (distance, subject) order).  Hits are sorted in the
+ * reference's print order.  --limit-per-sequence is a host-side run-length filter over this
+ * list (smafa_apply_limit_per_sequence). */
+int smafa_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q,
+                uint32_t q_len, int64_t max_divergence, int64_t max_num_hits, smafa_hit **hits,
+                uint64_t *n_hits, smafa_stats *stats);
+
+/* Same, with queries already in device memory and hits left in a caller-provided device
+ * buffer (capacity in rows).  *n_hits receives the number of rows the answer has; when it
+ * exceeds hits_capacity the call returns SMAFA_E_OOM and nothing useful is in hits_dev.
+ * Work is enqueued on `stream`; the call returns after the stream has been synchronised. */
+int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc_dev, uint64_t Q,
+                    uint32_t q_len, int64_t max_divergence, int64_t max_num_hits,
+                    smafa_hit *hits_dev, uint64_t hits_capacity, uint64_t *n_hits,
+                    void *stream, smafa_stats *stats);
+
+/* Multi-GPU merge: applies the reference's selection to the union of the
+ * per-shard candidate lists (after the NCCL all-gather).  In-place on a device buffer of n
+ * rows; *n_out rows remain, sorted in print order. */
+int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n, int64_t max_divergence,
+                    int64_t max_num_hits, uint64_t *n_out, void *stream);
+
+/* --limit-per-sequence (src/lib.rs:259-260,269-289): run-length cap over consecutive hits of
+ * one query whose subjects have identical encodings.  In-place on a host array; returns the
+ * new length.  db_enc is the host copy of the db words ([D][W]). */
+uint64_t smafa_apply_limit_per_sequence(smafa_hit *hits, uint64_t n, const uint64_t *db_enc,
+                                        uint32_t W, uint64_t subject_offset, uint32_t limit);
+
+/* ---- cluster (src/cluster.rs:45-74) -----------------------------------------------------
+ * enc: n encodings in input order, duplicates already removed (the HashSet step,
+ * src/cluster.rs:46-48, stays on the host).  centroid_of[i] receives the input index of the
+ * centroid sequence i joins (itself when it founds a new cluster).  The distance evaluation
+ * is batched on the GPU; the order-dependent greedy assignment is replayed exactly.
+ * n_comparisons (optional) receives sum_i |centroids before i|, the reference's work count. */
+int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L,
+                  uint32_t max_divergence, uint32_t *centroid_of, uint64_t *n_centroids,
+                  uint64_t *n_comparisons, smafa_stats *stats);
+
+void smafa_free(void *p);
+
+/* ---- host-side mirror of the reference's public functions (no GPU needed for makedb/count)
+ * Same argument meaning as smafa::makedb / query / cluster / count (src/lib.rs:137,198,378;
+ * src/cluster.rs:13).  Output goes to the given file descriptor.  On failure the return code
+ * says whether the reference would have exited 1 (SMAFA_E_IO) or panicked (any other code);
+ * smafa_last_error(NULL) holds the message. */
+int smafa_makedb_file(const char *subject_fasta, const char *db_path);
+int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fasta,
+                     int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
+                     int out_fd);
+int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd);
+int smafa_count_files(const char *const *paths, size_t n_paths, int out_fd);
+/* Opens a db file and applies the version gate of src/lib.rs:208-217 (no GPU needed). */
+int smafa_db_file_check(const char *db_path);
+
+/* Encoding helpers (src/lib.rs:29-52, 113-135, 167-196). */
+uint8_t smafa_encode_symbol(uint8_t byte); /* 0 == not a nucleotide */
+int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos);
+int smafa_decode_window(const uint64_t *words, size_t len, char *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAFA_B200_H */

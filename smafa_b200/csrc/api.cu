@@ -1,0 +1,730 @@
+// C ABI of libsmafa_b200.so: context / db management, query batching, overflow retry.
+// See include/smafa_b200.h for the contract and the reference code each entry point replaces.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+#include "kernels.h"
+
+using namespace smafa;
+
+static thread_local std::string g_err;  // ctx-less failures
+
+const char *smafa_global_error() { return g_err.c_str(); }
+void smafa_set_global_error(const std::string &s) { g_err = s; }
+
+static int fail(smafa_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SMAFA_E_OOM : SMAFA_E_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+
+extern "C" int smafa_abi_version(void) { return SMAFA_B200_ABI_VERSION; }
+
+extern "C" const char *smafa_status_name(int s) {
+  switch (s) {
+    case SMAFA_OK: return "SMAFA_OK";
+    case SMAFA_E_LENGTH_MISMATCH: return "SMAFA_E_LENGTH_MISMATCH";
+    case SMAFA_E_EMPTY_DB: return "SMAFA_E_EMPTY_DB";
+    case SMAFA_E_BAD_K: return "SMAFA_E_BAD_K";
+    case SMAFA_E_LIMIT_NEEDS_K: return "SMAFA_E_LIMIT_NEEDS_K";
+    case SMAFA_E_CUDA: return "SMAFA_E_CUDA";
+    case SMAFA_E_OOM: return "SMAFA_E_OOM";
+    case SMAFA_E_INVALID: return "SMAFA_E_INVALID";
+    case SMAFA_E_UNSUPPORTED: return "SMAFA_E_UNSUPPORTED";
+    case SMAFA_E_IO: return "SMAFA_E_IO";
+    case SMAFA_E_PANIC: return "SMAFA_E_PANIC";
+    default: return "SMAFA_E_?";
+  }
+}
+
+extern "C" const char *smafa_last_error(const smafa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" void smafa_free(void *p) { free(p); }
+
+// ------------------------------------------------------------------------------- context
+
+extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
+  smafa_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, SMAFA_E_INVALID, "smafa_ctx_create: null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, SMAFA_E_CUDA,
+                "no CUDA device available (%s); libsmafa_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, SMAFA_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, SMAFA_E_CUDA, "device %d is sm_%d%d; libsmafa_b200 holds sm_100a code only", device,
+                prop.major, prop.minor);
+  CU(cudaSetDevice(device));
+  ctx = new smafa_ctx();
+  ctx->device = device;
+  ctx->kernel = kernel;
+  ctx->num_sms = prop.multiProcessorCount;
+  cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
+  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  cudaHostAlloc((void **)&ctx->h_scalars, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+  cudaMalloc((void **)&ctx->d_scalars, 4 * sizeof(unsigned long long));
+  *out = ctx;
+  return SMAFA_OK;
+}
+
+static void free_workspace(smafa_ctx *ctx) {
+  cudaFree(ctx->cand); ctx->cand = nullptr;
+  cudaFree(ctx->fw.keys_sorted); cudaFree(ctx->fw.keys_sel); cudaFree(ctx->fw.cub_temp);
+  cudaFree(ctx->fw.seg_start); cudaFree(ctx->fw.seg_end);
+  ctx->fw = FinalizeWorkspace();
+  cudaFree(ctx->hits); ctx->hits = nullptr;
+  ctx->ws_cap = 0;
+}
+
+extern "C" void smafa_ctx_destroy(smafa_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_workspace(ctx);
+  cudaFree(ctx->bound); cudaFree(ctx->hist); cudaFree(ctx->q_ref); cudaFree(ctx->q_planes);
+  cudaFree(ctx->q_onehot);
+  cudaFree(ctx->d_scalars);
+  cudaFreeHost(ctx->h_scalars);
+  for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel) {
+  if (!ctx || kernel < 0 || kernel > 2) return fail(ctx, SMAFA_E_INVALID, "bad kernel selector %d", kernel);
+  ctx->kernel = kernel;
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows) {
+  if (!ctx) return SMAFA_E_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_workspace(ctx);
+  ctx->cand_cap_request = rows;
+  return SMAFA_OK;
+}
+
+// Candidate / finalize workspace for `rows` candidate rows.
+static int ensure_workspace(smafa_ctx *ctx, uint64_t rows) {
+  if (ctx->ws_cap >= rows) return SMAFA_OK;
+  cudaStreamSynchronize(ctx->stream);
+  free_workspace(ctx);
+  CU(cudaMalloc((void **)&ctx->cand, rows * sizeof(uint64_t)));
+  CU(cudaMalloc((void **)&ctx->fw.keys_sorted, rows * sizeof(uint64_t)));
+  CU(cudaMalloc((void **)&ctx->fw.keys_sel, rows * sizeof(uint64_t)));
+  CU(cudaMalloc((void **)&ctx->fw.seg_start, MAX_BATCH_QUERIES * sizeof(uint32_t)));
+  CU(cudaMalloc((void **)&ctx->fw.seg_end, MAX_BATCH_QUERIES * sizeof(uint32_t)));
+  ctx->fw.cub_temp_bytes = finalize_temp_bytes(rows);
+  CU(cudaMalloc(&ctx->fw.cub_temp, ctx->fw.cub_temp_bytes));
+  ctx->fw.n_selected = ctx->d_scalars + 1;
+  ctx->fw.cap = rows;
+  CU(cudaMalloc((void **)&ctx->hits, rows * sizeof(smafa_hit)));
+  ctx->ws_cap = rows;
+  return SMAFA_OK;
+}
+
+template <class T>
+static int ensure_buf(smafa_ctx *ctx, T *&ptr, size_t &cap, size_t need) {
+  if (cap >= need) return SMAFA_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  CU(cudaMalloc((void **)&ptr, need * sizeof(T)));
+  cap = need;
+  return SMAFA_OK;
+}
+
+// ------------------------------------------------------------------------------- db
+
+static uint32_t words_for(uint32_t L) { return (L + 11) / 12; }
+static uint32_t row_words_for(uint32_t L) { return L <= 32 ? 4 : (L <= 64 ? 8 : 0); }
+
+static int db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
+  if (rows <= db->cap) return SMAFA_OK;
+  uint64_t ncap = std::max<uint64_t>(rows, db->cap * 2);
+  ncap = (ncap + 255) / 256 * 256;
+  uint64_t *nref = nullptr;
+  uint32_t *npl = nullptr;
+  CU(cudaMalloc((void **)&nref, std::max<uint64_t>(1, ncap * db->W) * sizeof(uint64_t)));
+  if (db->row_words) {
+    // one extra tile of rows so the POPC kernel's register prefetch never leaves the allocation
+    size_t bytes = (ncap + 512) * db->row_words * sizeof(uint32_t);
+    CU(cudaMalloc((void **)&npl, bytes));
+    CU(cudaMemsetAsync(npl, 0, bytes, ctx->stream));
+  }
+  if (db->D) {
+    CU(cudaMemcpyAsync(nref, db->ref, db->D * db->W * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (db->row_words)
+      CU(cudaMemcpyAsync(npl, db->planes, db->D * db->row_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                         ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(db->ref);
+  cudaFree(db->planes);
+  db->ref = nref;
+  db->planes = npl;
+  db->cap = ncap;
+  int rc = mma_db_reserve(ctx, db, ncap);
+  return rc;
+}
+
+static int db_add_rows(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n) {
+  if (n == 0) return SMAFA_OK;
+  if (db->D + n >= (1ull << 32)) return fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
+  int rc = db_reserve(ctx, db, db->D + n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(db->ref + db->D * db->W, enc, n * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (db->row_words)
+    launch_pack_planes(db->ref + db->D * db->W, (uint32_t)n, db->W, db->L, db->row_words,
+                       db->planes + db->D * db->row_words, db->invalid_flag, ctx->stream);
+  rc = mma_db_pack(ctx, db, db->D, n);
+  if (rc) return rc;
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, db->invalid_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  if (flag) db->generic_only = true;
+  db->D += n;
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset,
+                               smafa_db **out) {
+  if (!ctx || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: null argument");
+  *out = nullptr;
+  if (D > 0 && (!enc || L == 0)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: D > 0 needs enc and L > 0");
+  if (L > MAX_WINDOW_LEN) return fail(ctx, SMAFA_E_UNSUPPORTED, "window length %u > %u", L, MAX_WINDOW_LEN);
+  CU(cudaSetDevice(ctx->device));
+  smafa_db *db = new smafa_db();
+  db->ctx = ctx;
+  db->L = L;
+  db->W = words_for(L);
+  db->row_words = row_words_for(L);
+  db->generic_only = (db->row_words == 0);
+  db->subject_offset = subject_offset;
+  cudaError_t e = cudaMalloc((void **)&db->invalid_flag, sizeof(int));
+  if (e != cudaSuccess) { delete db; return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  cudaMemsetAsync(db->invalid_flag, 0, sizeof(int), ctx->stream);
+  int rc = db_add_rows(ctx, db, enc, D);
+  if (rc) { smafa_db_free(db); return rc; }
+  *out = db;
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n) {
+  if (!ctx || !db || (n && !enc)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_append: null argument");
+  CU(cudaSetDevice(ctx->device));
+  return db_add_rows(ctx, db, enc, n);
+}
+
+extern "C" uint64_t smafa_db_size(const smafa_db *db) { return db ? db->D : 0; }
+extern "C" uint32_t smafa_db_window_len(const smafa_db *db) { return db ? db->L : 0; }
+
+extern "C" void smafa_db_free(smafa_db *db) {
+  if (!db) return;
+  if (db->ctx) { cudaSetDevice(db->ctx->device); cudaStreamSynchronize(db->ctx->stream); }
+  cudaFree(db->ref);
+  cudaFree(db->planes);
+  cudaFree(db->invalid_flag);
+  mma_db_free(db);
+  delete db;
+}
+
+// ------------------------------------------------------------------------------- distances
+
+extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len,
+                               uint16_t *out) {
+  if (!ctx || !db) return fail(ctx, SMAFA_E_INVALID, "smafa_distances: null argument");
+  if (Q == 0 || db->D == 0) return SMAFA_OK;
+  if (!q_enc || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_distances: null buffer");
+  if (q_len != db->L)
+    return fail(ctx, SMAFA_E_LENGTH_MISMATCH,
+                "Cannot compute distances between seq of length %u and windows of lengths %u", q_len, db->L);
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t D = db->D;
+  uint64_t qb = std::max<uint64_t>(1, std::min<uint64_t>(Q, (1ull << 29) / D));  // <= 1 GiB of u16 per batch
+  uint64_t *dq = nullptr;
+  uint16_t *dout = nullptr;
+  CU(cudaMalloc((void **)&dq, qb * db->W * sizeof(uint64_t)));
+  cudaError_t e = cudaMalloc((void **)&dout, qb * D * sizeof(uint16_t));
+  if (e != cudaSuccess) { cudaFree(dq); return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  int rc = SMAFA_OK;
+  for (uint64_t q0 = 0; q0 < Q && rc == SMAFA_OK; q0 += qb) {
+    uint64_t nq = std::min(qb, Q - q0);
+    cudaMemcpyAsync(dq, q_enc + q0 * db->W, nq * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    launch_distances(dq, (uint32_t)nq, db->ref, (uint32_t)D, db->W, dout, ctx->stream);
+    cudaMemcpyAsync(out + q0 * D, dout, nq * D * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (e2 != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "smafa_distances: %s", cudaGetErrorString(e2));
+  }
+  cudaFree(dq);
+  cudaFree(dout);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------- query
+
+namespace {
+
+struct QueryPlan {
+  int mode;        // ScanMode
+  uint32_t k_scan; // MODE_KTH tightening parameter
+  uint32_t k_fin;  // finalize: keep rows <= k-th smallest distance (UINT32_MAX: keep all)
+  int bound0;      // initial bound
+};
+
+constexpr int RC_OVERFLOW = 1;  // internal: candidate buffer too small for this batch
+
+}  // namespace
+
+static int validate_query(smafa_ctx *ctx, const smafa_db *db, uint64_t Q, uint32_t q_len, int64_t m, int64_t k,
+                          QueryPlan *plan) {
+  if (Q == 0) return SMAFA_OK;
+  // order of the reference's checks for the first record: length (src/lib.rs:72-79), then the
+  // selection's unwrap()/underflow panics (src/lib.rs:253-255,298)
+  if (db->D > 0 && q_len != db->L)
+    return fail(ctx, SMAFA_E_LENGTH_MISMATCH,
+                "Cannot compute distances between seq of length %u and windows of lengths %u", q_len, db->L);
+  const bool mode_b = (k >= 0 && k != 1);  // src/lib.rs:224
+  if (mode_b && k == 0 && db->D > 0) return fail(ctx, SMAFA_E_BAD_K, "attempt to subtract with overflow");
+  if (db->D == 0) return fail(ctx, SMAFA_E_EMPTY_DB, "called `Option::unwrap()` on a `None` value");
+  plan->bound0 = (int)db->L;
+  if (m >= 0 && m < (int64_t)db->L) plan->bound0 = (int)m;
+  if (!mode_b) {
+    plan->mode = MODE_MIN;
+    plan->k_scan = 1;
+    plan->k_fin = 1;
+  } else if ((uint64_t)k >= db->D) {  // cutoff = largest distance (src/lib.rs:254): nothing to tighten
+    plan->mode = MODE_FIXED;
+    plan->k_scan = 0;
+    plan->k_fin = UINT32_MAX;
+  } else {
+    plan->mode = MODE_KTH;
+    plan->k_scan = (uint32_t)k;
+    plan->k_fin = (uint32_t)k;
+  }
+  return SMAFA_OK;
+}
+
+static uint32_t pick_chunk(const smafa_ctx *ctx, uint64_t D, uint64_t n_qtiles, uint32_t tile) {
+  // aim at >= 8 blocks per SM-slot so the tail wave is short; never below one tile
+  uint64_t target_blocks = (uint64_t)ctx->num_sms * 3 * 8;
+  uint64_t chunks = std::max<uint64_t>(1, target_blocks / std::max<uint64_t>(1, n_qtiles));
+  uint64_t chunk = (D + chunks - 1) / chunks;
+  chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, tile), 16384);
+  return (uint32_t)((chunk + tile - 1) / tile * tile);
+}
+
+// One batch (<= 2^20 queries, words already on the device).  Leaves *n_rows rows in ctx->hits.
+static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
+                     const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st) {
+  int rc;
+  uint64_t want_cap = ctx->cand_cap_request ? ctx->cand_cap_request : DEFAULT_CAND_CAP;
+  if ((rc = ensure_workspace(ctx, std::max<uint64_t>(want_cap, ctx->ws_cap)))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, Qb))) return rc;
+  launch_init_bound(ctx->bound, Qb, plan.bound0, s);
+  uint32_t hist_stride = db->L + 1;
+  if (plan.mode == MODE_KTH) {
+    if ((rc = ensure_buf(ctx, ctx->hist, ctx->hist_cap, (size_t)Qb * hist_stride))) return rc;
+    CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
+  }
+  unsigned long long *cand_count = ctx->d_scalars + 0;
+  CU(cudaMemsetAsync(cand_count, 0, sizeof(unsigned long long), s));
+
+  ScanParams p{};
+  p.q_ref = q_ref_dev;
+  p.Q = Qb;
+  p.d_planes = db->planes;
+  p.d_ref = db->ref;
+  p.D = (uint32_t)db->D;
+  p.d_begin = 0;
+  p.d_end = (uint32_t)db->D;
+  p.W = db->W;
+  p.L = db->L;
+  p.mode = plan.mode;
+  p.k = plan.k_scan;
+  p.bound = ctx->bound;
+  p.hist = ctx->hist;
+  p.hist_stride = hist_stride;
+  p.cand = ctx->cand;
+  p.cand_count = cand_count;
+  p.cand_cap = ctx->ws_cap;
+
+  int kernel = ctx->kernel;
+  if (db->generic_only) kernel = -1;
+  else if (kernel == SMAFA_KERNEL_AUTO) kernel = mma_supported(db) && ctx->auto_prefers_mma ? SMAFA_KERNEL_MMA : SMAFA_KERNEL_POPC;
+  if (kernel == SMAFA_KERNEL_MMA && !mma_supported(db)) kernel = SMAFA_KERNEL_POPC;
+
+  uint64_t n_cand = 0;
+  for (;;) {
+    int *q_invalid = ctx->d_scratch_flag();
+    CU(cudaMemsetAsync(q_invalid, 0, sizeof(int), s));
+    cudaEventRecord(ctx->ev[0], s);
+    int launches = 2;
+    if (kernel == -1) {
+      uint32_t chunk = pick_chunk(ctx, db->D, (Qb + 127) / 128, 256);
+      launches += launch_scan_generic(p, chunk, s);
+    } else {
+      if ((rc = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)Qb + 256) * db->row_words))) return rc;
+      launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, ctx->q_planes, q_invalid, s);
+      launches += 1;
+      p.q_planes = ctx->q_planes;
+      if (kernel == SMAFA_KERNEL_MMA) {
+        int l = mma_scan(ctx, db, p, s);
+        if (l < 0) return l;
+        launches += l;
+      } else {
+        const bool early = plan.bound0 * 4 <= (int)db->L;
+        uint32_t r = Qb >= 148u * 256u * 2u ? 4 : 1;
+        uint32_t chunk = pick_chunk(ctx, db->D, (Qb + 256 * r - 1) / (256 * r), popc_tile_rows());
+        launches += launch_scan_popc(p, early, chunk, s);
+      }
+    }
+    cudaEventRecord(ctx->ev[1], s);
+    CU(cudaMemcpyAsync(ctx->h_scalars + 0, cand_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    n_cand = ctx->h_scalars[0];
+    if (st) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+      st->scan_ms += ms;
+      st->kernel_used = kernel == -1 ? 0 : (uint32_t)kernel;
+      st->kernel_launches += launches;
+    }
+    if (kernel != -1 && (int)(ctx->h_scalars[2] & 0xffffffffu) != 0) {
+      // a query holds words that are not valid one-hot codes: redo the batch on the reference
+      // word layout, which reproduces popcount(a^b)/2 for arbitrary words
+      kernel = -1;
+      launch_init_bound(ctx->bound, Qb, plan.bound0, s);
+      if (plan.mode == MODE_KTH) CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
+      CU(cudaMemsetAsync(cand_count, 0, sizeof(unsigned long long), s));
+      continue;
+    }
+    break;
+  }
+  if (st) st->candidates += n_cand;
+  if (n_cand > ctx->ws_cap) return RC_OVERFLOW;
+  int fl = launch_finalize(ctx->fw, ctx->cand, n_cand, Qb, plan.k_fin, q_base, db->subject_offset, ctx->hits,
+                           ctx->ws_cap, ctx->h_scalars + 1, s);
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  if (st) st->kernel_launches += fl;
+  *n_rows = ctx->h_scalars[1];
+  return SMAFA_OK;
+}
+
+// Runs [q0, q0+n) of the device-resident queries, splitting on candidate overflow.  `sink` gets
+// each finished batch (rows in ctx->hits).
+template <class Sink>
+static int run_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint64_t q0, uint64_t n, uint64_t q_base,
+                     const QueryPlan &plan, cudaStream_t s, smafa_stats *st, Sink &&sink) {
+  uint64_t done = 0;
+  while (done < n) {
+    uint64_t nb = std::min<uint64_t>(n - done, MAX_BATCH_QUERIES);
+    for (;;) {
+      uint64_t rows = 0;
+      int rc = run_batch(ctx, db, q_dev + (q0 + done) * db->W, (uint32_t)nb, (uint32_t)(q_base + q0 + done), plan, &rows, s, st);
+      if (rc == RC_OVERFLOW) {
+        if (st) st->retries++;
+        if (nb == 1) {  // a single query can emit at most D rows
+          int r2 = ensure_workspace(ctx, std::max<uint64_t>(ctx->ws_cap * 2, db->D + 1024));
+          if (r2) return r2;
+          ctx->cand_cap_request = 0;
+        } else {
+          nb = (nb + 1) / 2;
+        }
+        continue;
+      }
+      if (rc) return rc;
+      rc = sink(rows);
+      if (rc) return rc;
+      break;
+    }
+    done += nb;
+  }
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len,
+                           int64_t m, int64_t k, smafa_hit **hits, uint64_t *n_hits, smafa_stats *stats) {
+  if (!ctx || !db || !hits || !n_hits) return fail(ctx, SMAFA_E_INVALID, "smafa_query: null argument");
+  *hits = nullptr;
+  *n_hits = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  QueryPlan plan{};
+  int rc = validate_query(ctx, db, Q, q_len, m, k, &plan);
+  if (rc || Q == 0) return rc;
+  if (!q_enc) return fail(ctx, SMAFA_E_INVALID, "smafa_query: null query buffer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  cudaEventRecord(ctx->ev[2], s);
+  std::vector<smafa_hit> all;
+  const uint64_t slab = MAX_BATCH_QUERIES;
+  for (uint64_t q0 = 0; q0 < Q; q0 += slab) {
+    uint64_t nq = std::min(slab, Q - q0);
+    if ((rc = ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, nq * db->W))) return rc;
+    CU(cudaMemcpyAsync(ctx->q_ref, q_enc + q0 * db->W, nq * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    rc = run_range(ctx, db, ctx->q_ref, 0, nq, q0, plan, s, stats, [&](uint64_t rows) -> int {
+      size_t old = all.size();
+      all.resize(old + rows);
+      if (rows) {
+        cudaError_t e = cudaMemcpyAsync(all.data() + old, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2H of hits: %s", cudaGetErrorString(e));
+      }
+      return SMAFA_OK;
+    });
+    if (rc) return rc;
+  }
+  cudaEventRecord(ctx->ev[3], s);
+  cudaEventSynchronize(ctx->ev[3]);
+  if (stats) {
+    cudaEventElapsedTime(&stats->total_ms, ctx->ev[2], ctx->ev[3]);
+    stats->pairs = Q * db->D;
+  }
+  smafa_hit *out = (smafa_hit *)malloc(std::max<size_t>(1, all.size()) * sizeof(smafa_hit));
+  if (!out) return fail(ctx, SMAFA_E_OOM, "malloc of %zu hits failed", all.size());
+  memcpy(out, all.data(), all.size() * sizeof(smafa_hit));
+  *hits = out;
+  *n_hits = all.size();
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc_dev, uint64_t Q, uint32_t q_len,
+                               int64_t m, int64_t k, smafa_hit *hits_dev, uint64_t hits_capacity, uint64_t *n_hits,
+                               void *stream, smafa_stats *stats) {
+  if (!ctx || !db || !n_hits) return fail(ctx, SMAFA_E_INVALID, "smafa_query_dev: null argument");
+  *n_hits = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  QueryPlan plan{};
+  int rc = validate_query(ctx, db, Q, q_len, m, k, &plan);
+  if (rc || Q == 0) return rc;
+  if (!q_enc_dev) return fail(ctx, SMAFA_E_INVALID, "smafa_query_dev: null query buffer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaEventRecord(ctx->ev[2], s);
+  uint64_t total = 0;
+  rc = run_range(ctx, db, q_enc_dev, 0, Q, 0, plan, s, stats, [&](uint64_t rows) -> int {
+    if (rows && hits_dev && total + rows <= hits_capacity) {
+      cudaError_t e = cudaMemcpyAsync(hits_dev + total, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2D of hits: %s", cudaGetErrorString(e));
+    }
+    total += rows;
+    return SMAFA_OK;
+  });
+  if (rc) return rc;
+  cudaEventRecord(ctx->ev[3], s);
+  cudaEventSynchronize(ctx->ev[3]);
+  if (stats) {
+    cudaEventElapsedTime(&stats->total_ms, ctx->ev[2], ctx->ev[3]);
+    stats->pairs = Q * db->D;
+  }
+  *n_hits = total;
+  if (total > hits_capacity)
+    return fail(ctx, SMAFA_E_OOM, "hits buffer too small: %llu rows needed, capacity %llu", (unsigned long long)total,
+                (unsigned long long)hits_capacity);
+  return SMAFA_OK;
+}
+
+extern "C" int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n, int64_t m, int64_t k, uint64_t *n_out,
+                               void *stream) {
+  if (!ctx || !n_out) return fail(ctx, SMAFA_E_INVALID, "smafa_merge_dev: null argument");
+  *n_out = 0;
+  if (n == 0) return SMAFA_OK;
+  if (!cands_dev) return fail(ctx, SMAFA_E_INVALID, "smafa_merge_dev: null buffer");
+  (void)m;  // every shard already applied --max-divergence
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc = ensure_workspace(ctx, std::max<uint64_t>({n, ctx->ws_cap, (uint64_t)1 << 20}));
+  if (rc) return rc;
+  const bool mode_b = (k >= 0 && k != 1);
+  uint32_t k_fin = mode_b ? (uint32_t)std::min<int64_t>(k, UINT32_MAX) : 1;
+  if (mode_b && k == 0) return fail(ctx, SMAFA_E_BAD_K, "attempt to subtract with overflow");
+  int *bad = ctx->d_scratch_flag();
+  CU(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  launch_hits_to_keys(cands_dev, n, ctx->cand, bad, s);
+  launch_finalize(ctx->fw, ctx->cand, n, MAX_BATCH_QUERIES, k_fin, 0, 0, ctx->hits, ctx->ws_cap, ctx->h_scalars + 1, s);
+  int hbad = 0;
+  CU(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  if (hbad) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_merge_dev: query index >= 2^20 or distance >= 4096 in one call");
+  uint64_t rows = ctx->h_scalars[1];
+  CU(cudaMemcpyAsync(cands_dev, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  *n_out = rows;
+  return SMAFA_OK;
+}
+
+extern "C" uint64_t smafa_apply_limit_per_sequence(smafa_hit *hits, uint64_t n, const uint64_t *db_enc, uint32_t W,
+                                                   uint64_t subject_offset, uint32_t limit) {
+  // src/lib.rs:259-260,269-289: the run is keyed on the decoded subject string, i.e. on the
+  // encoding; a skipped hit does not reset the run; a new query starts with no run.
+  uint64_t o = 0;
+  const uint64_t *last = nullptr;
+  uint32_t count = 0, last_q = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t *enc = db_enc + ((uint64_t)hits[i].subject - subject_offset) * W;
+    if (i == 0 || hits[i].query != last_q) { last = nullptr; count = 0; last_q = hits[i].query; }
+    if (last && memcmp(last, enc, W * sizeof(uint64_t)) == 0) {
+      if (count >= limit) continue;
+      count++;
+    } else {
+      last = enc;
+      count = 1;
+    }
+    hits[o++] = hits[i];
+  }
+  return o;
+}
+
+// ------------------------------------------------------------------------------- cluster
+
+// src/cluster.rs:45-74 with the distance evaluation batched on the GPU.
+//
+// The greedy is order dependent: sequence i sees every centroid founded by sequences < i.  For a
+// batch [b0,b1) the GPU evaluates (1) batch x existing centroids -- Mode A with --max-divergence t,
+// i.e. per sequence the minimum distance and the lowest centroid index at it, only if <= t -- and
+// (2) batch x batch with a fixed bound t (every pair within t).  The host then replays the batch
+// sequentially: a sequence joins the nearest centroid among the old ones and the in-batch
+// sequences that became centroids before it (ties -> lowest centroid index, src/cluster.rs:62-68:
+// old centroids always have lower indices than in-batch ones), else founds a new centroid.
+extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t,
+                             uint32_t *centroid_of, uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats) {
+  if (!ctx || (n && (!enc || !centroid_of))) return fail(ctx, SMAFA_E_INVALID, "smafa_cluster: null argument");
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (n_centroids) *n_centroids = 0;
+  if (n_comparisons) *n_comparisons = 0;
+  if (n == 0) return SMAFA_OK;
+  if (L == 0) return fail(ctx, SMAFA_E_INVALID, "smafa_cluster: L == 0");
+  if (n >= (1ull << 32)) return fail(ctx, SMAFA_E_UNSUPPORTED, "more than 2^32-1 sequences");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const uint32_t W = words_for(L);
+  smafa_db *cdb = nullptr, *bdb = nullptr;
+  int rc = smafa_db_upload(ctx, nullptr, 0, L, 0, &cdb);
+  if (!rc) rc = smafa_db_upload(ctx, nullptr, 0, L, 0, &bdb);
+  std::vector<uint32_t> cent_input;          // centroid number -> input index
+  std::vector<int64_t> cent_of_input_batch;  // in-batch: centroid number founded by batch row, or -1
+  std::vector<smafa_hit> old_hits, in_hits;
+  std::vector<uint64_t> new_words;
+  uint64_t comparisons = 0, pairs = 0;
+  cudaEventRecord(ctx->ev[2], s);
+
+  QueryPlan plan_old{MODE_MIN, 1, 1, (int)std::min<uint32_t>(t, L)};
+  QueryPlan plan_in{MODE_FIXED, 0, UINT32_MAX, (int)std::min<uint32_t>(t, L)};
+
+  for (uint64_t b0 = 0; b0 < n && !rc;) {
+    const uint64_t C = cent_input.size();
+    uint64_t B = std::min<uint64_t>(std::max<uint64_t>(4096, C / 2), 65536);
+    B = std::min(B, n - b0);
+    const uint64_t *benc = enc + b0 * W;
+    // batch rows as queries (device copy) and as a db
+    if ((rc = ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, B * W))) break;
+    cudaMemcpyAsync(ctx->q_ref, benc, B * W * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+    bdb->D = 0;
+    if ((rc = db_add_rows(ctx, bdb, benc, B))) break;
+
+    old_hits.clear();
+    in_hits.clear();
+    auto collect = [&](std::vector<smafa_hit> &dst) {
+      return [&dst, ctx, s](uint64_t rows) -> int {
+        size_t old = dst.size();
+        dst.resize(old + rows);
+        if (rows) {
+          cudaError_t e = cudaMemcpyAsync(dst.data() + old, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToHost, s);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+          if (e != cudaSuccess) return SMAFA_E_CUDA;
+        }
+        return SMAFA_OK;
+      };
+    };
+    if (C > 0) {
+      rc = run_range(ctx, cdb, ctx->q_ref, 0, B, 0, plan_old, s, stats, collect(old_hits));
+      if (rc) break;
+      pairs += B * C;
+    }
+    rc = run_range(ctx, bdb, ctx->q_ref, 0, B, 0, plan_in, s, stats, collect(in_hits));
+    if (rc) break;
+    pairs += B * B;
+
+    // sequential replay (hits are sorted by (query, distance, subject))
+    cent_of_input_batch.assign(B, -1);
+    new_words.clear();
+    size_t po = 0, pi = 0;
+    for (uint64_t i = 0; i < B; ++i) {
+      comparisons += cent_input.size();
+      int64_t best_c = -1;
+      uint32_t best_d = UINT32_MAX;
+      while (po < old_hits.size() && old_hits[po].query < i) ++po;
+      if (po < old_hits.size() && old_hits[po].query == i) {  // first row = lowest centroid at the minimum
+        best_d = old_hits[po].distance;
+        best_c = old_hits[po].subject;
+      }
+      while (pi < in_hits.size() && in_hits[pi].query < i) ++pi;
+      for (size_t h = pi; h < in_hits.size() && in_hits[h].query == i; ++h) {
+        const smafa_hit &x = in_hits[h];
+        if (x.distance >= best_d) break;  // sorted by distance; old centroids win ties
+        if (x.subject < i && cent_of_input_batch[x.subject] >= 0) {
+          best_d = x.distance;  // first in (distance, subject) order = lowest in-batch centroid
+          best_c = cent_of_input_batch[x.subject];
+          break;
+        }
+      }
+      if (best_c >= 0 && best_d <= t) {
+        centroid_of[b0 + i] = cent_input[(size_t)best_c];
+      } else {
+        cent_of_input_batch[i] = (int64_t)cent_input.size();
+        cent_input.push_back((uint32_t)(b0 + i));
+        centroid_of[b0 + i] = (uint32_t)(b0 + i);
+        new_words.insert(new_words.end(), benc + i * W, benc + (i + 1) * W);
+      }
+    }
+    if (!new_words.empty()) rc = db_add_rows(ctx, cdb, new_words.data(), new_words.size() / W);
+    b0 += B;
+  }
+  cudaEventRecord(ctx->ev[3], s);
+  cudaEventSynchronize(ctx->ev[3]);
+  if (stats) {
+    cudaEventElapsedTime(&stats->total_ms, ctx->ev[2], ctx->ev[3]);
+    stats->pairs = pairs;
+  }
+  if (cdb) smafa_db_free(cdb);
+  if (bdb) smafa_db_free(bdb);
+  if (rc == SMAFA_E_CUDA && ctx->err.empty()) fail(ctx, rc, "smafa_cluster: CUDA failure");
+  if (rc) return rc;
+  if (n_centroids) *n_centroids = cent_input.size();
+  if (n_comparisons) *n_comparisons = comparisons;
+  return SMAFA_OK;
+}

@@ -1,0 +1,92 @@
+// Shared device-side definitions of the smafa B200 hot path.
+//
+// Protocol shared by both scan formulations (POPC and tcgen05 MMA):
+//   every query q of the current batch has a running `bound[q]` = the largest distance that can
+//   still be part of the answer.  A scan kernel must emit EVERY db window whose distance is
+//   <= the final bound (it may emit more: the bound only ever decreases, emission tests against
+//   a possibly stale, i.e. larger, value).  finalize.cu then applies the reference's exact
+//   cutoff (src/lib.rs:253-265,298-312) to the emitted superset.
+//
+//   MODE_FIXED : bound never moves (cluster's in-batch pass: everything within t)
+//   MODE_MIN   : bound = min(bound, d)                      -> "Mode A", src/lib.rs:296-314
+//   MODE_KTH   : bound = smallest t with #(d <= t) >= k     -> "Mode B", src/lib.rs:242-265
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smafa {
+
+enum ScanMode : int { MODE_FIXED = 0, MODE_MIN = 1, MODE_KTH = 2 };
+
+// Candidate rows are stored as one sortable 64-bit key:
+//   bits 63..44 query (batch-local, < 2^20) | bits 43..32 distance (< 2^12) | bits 31..0 subject
+constexpr int KEY_Q_SHIFT = 44;
+constexpr int KEY_D_SHIFT = 32;
+constexpr uint32_t KEY_D_MASK = 0xFFFu;
+constexpr uint32_t MAX_BATCH_QUERIES = 1u << 20;
+constexpr uint32_t MAX_WINDOW_LEN = 4095;
+
+__host__ __device__ inline uint64_t make_key(uint32_t q, uint32_t d, uint32_t j) {
+  return ((uint64_t)q << KEY_Q_SHIFT) | ((uint64_t)d << KEY_D_SHIFT) | (uint64_t)j;
+}
+__host__ __device__ inline uint32_t key_q(uint64_t k) { return (uint32_t)(k >> KEY_Q_SHIFT); }
+__host__ __device__ inline uint32_t key_d(uint64_t k) { return (uint32_t)(k >> KEY_D_SHIFT) & KEY_D_MASK; }
+__host__ __device__ inline uint32_t key_j(uint64_t k) { return (uint32_t)k; }
+
+struct ScanParams {
+  // queries of this batch
+  const uint32_t *q_planes;  // [Qpad][row_words] bit planes (see pack.cu)
+  const uint64_t *q_ref;     // [Q][W] reference-layout words
+  uint32_t Q;
+  // db (or db shard)
+  const uint32_t *d_planes;  // [Dpad][row_words]
+  const uint64_t *d_ref;     // [D][W]
+  uint32_t D;
+  uint32_t d_begin, d_end;   // window range covered by this launch
+  uint32_t W, L;
+  // running state
+  int mode;
+  uint32_t k;                // MODE_KTH
+  int *bound;                // [Q]; signed so that "no candidates" can be expressed as -1
+  uint32_t *hist;            // [Q][hist_stride] (MODE_KTH) else nullptr
+  uint32_t hist_stride;
+  uint64_t *cand;            // candidate keys
+  unsigned long long *cand_count;
+  uint64_t cand_cap;
+};
+
+// Slow path shared by all scan kernels: record a candidate and tighten the query's bound.
+// `bound` is the caller's private copy (register); the global copy is updated with atomicMin so
+// that blocks working on other db ranges of the same query start from the tightened value.
+__device__ __forceinline__ void emit_candidate(const ScanParams &p, uint32_t q, uint32_t j, int d, int &bound) {
+  unsigned long long slot = atomicAdd(p.cand_count, 1ull);
+  if (slot < p.cand_cap) p.cand[slot] = make_key(q, (uint32_t)d, j);
+  if (p.mode == MODE_MIN) {
+    if (d < bound) {
+      bound = d;
+      atomicMin(p.bound + q, d);
+    }
+  } else if (p.mode == MODE_KTH) {
+    uint32_t *h = p.hist + (size_t)q * p.hist_stride;
+    atomicAdd(h + d, 1u);
+    uint32_t cum = 0;
+    int nb = bound;
+    for (int t = 0; t <= bound; ++t) {
+      cum += __ldcg(h + t);
+      if (cum >= p.k) { nb = t; break; }
+    }
+    if (nb < bound) {
+      bound = nb;
+      atomicMin(p.bound + q, nb);
+    }
+  }
+}
+
+// Exact reference distance on the reference word layout (src/lib.rs:80-88).
+__device__ __forceinline__ int ref_distance(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint32_t W) {
+  int s = 0;
+  for (uint32_t w = 0; w < W; ++w) s += __popcll(a[w] ^ b[w]);
+  return s >> 1;
+}
+
+}  // namespace smafa

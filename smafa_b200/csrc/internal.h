@@ -1,0 +1,60 @@
+// Internal host-side state behind the opaque handles of include/smafa_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "kernels.h"
+
+constexpr uint64_t DEFAULT_CAND_CAP = 32ull << 20;  // candidate rows per batch (8 B each)
+
+struct smafa_ctx {
+  int device = 0;
+  int kernel = 0;
+  int num_sms = 148;
+  bool auto_prefers_mma = false;  // set from the measured comparison (profiles/), see DESIGN.md
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {};
+  std::string err;
+  // candidate + finalize workspace
+  uint64_t cand_cap_request = 0;
+  uint64_t ws_cap = 0;
+  uint64_t *cand = nullptr;
+  smafa::FinalizeWorkspace fw;
+  smafa_hit *hits = nullptr;
+  // per-batch query state
+  int *bound = nullptr;           size_t bound_cap = 0;
+  uint32_t *hist = nullptr;       size_t hist_cap = 0;
+  uint64_t *q_ref = nullptr;      size_t q_ref_cap = 0;
+  uint32_t *q_planes = nullptr;   size_t q_planes_cap = 0;
+  uint8_t *q_onehot = nullptr;    size_t q_onehot_cap = 0;
+  // scalars: [0] candidate count, [1] selected count, [2] scratch flag, [3] spare
+  unsigned long long *d_scalars = nullptr;
+  unsigned long long *h_scalars = nullptr;  // pinned mirror
+  int *d_scratch_flag() { return reinterpret_cast<int *>(d_scalars + 2); }
+};
+
+struct smafa_db {
+  smafa_ctx *ctx = nullptr;
+  uint64_t D = 0, cap = 0;
+  uint32_t L = 0, W = 0, row_words = 0;
+  uint64_t subject_offset = 0;
+  bool generic_only = false;  // invalid codes or L > 64: reference-layout kernel only
+  uint64_t *ref = nullptr;    // [cap][W]
+  uint32_t *planes = nullptr; // [cap + pad][row_words]
+  int *invalid_flag = nullptr;
+  // tcgen05 operand (scan_mma.cu)
+  uint8_t *onehot = nullptr;
+  uint64_t onehot_cap = 0;
+};
+
+const char *smafa_global_error();
+void smafa_set_global_error(const std::string &s);
+
+// scan_mma.cu
+bool mma_supported(const smafa_db *db);
+int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows);
+int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n);
+void mma_db_free(smafa_db *db);
+// returns kernels launched (>= 0) or a negative smafa_status
+int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s);

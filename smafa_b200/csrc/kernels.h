@@ -1,0 +1,45 @@
+// Host-callable launchers of the device code (internal; the public boundary is include/smafa_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/smafa_b200.h"
+
+namespace smafa {
+
+struct ScanParams;
+
+// pack.cu
+void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words,
+                        uint32_t *planes, int *invalid, cudaStream_t s);
+void launch_init_bound(int *bound, uint32_t Q, int v, cudaStream_t s);
+
+// scan_popc.cu -- return the number of kernels launched
+int launch_scan_popc(const ScanParams &p, bool early, uint32_t chunk, cudaStream_t s);
+int launch_scan_generic(const ScanParams &p, uint32_t chunk, cudaStream_t s);
+void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W,
+                      uint16_t *out, cudaStream_t s);
+int popc_tile_rows();
+
+// finalize.cu
+struct FinalizeWorkspace {
+  uint64_t *keys_sorted = nullptr;  // [cap]
+  uint64_t *keys_sel = nullptr;     // [cap]
+  uint32_t *seg_start = nullptr;    // [MAX_BATCH_QUERIES]
+  uint32_t *seg_end = nullptr;      // [MAX_BATCH_QUERIES]
+  unsigned long long *n_selected = nullptr;  // device scalar
+  void *cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+  uint64_t cap = 0;
+};
+size_t finalize_temp_bytes(uint64_t cap);
+// Sorts n candidate keys by (query, distance, subject), keeps per query everything <= the k-th
+// smallest distance (k = UINT32_MAX keeps all) and writes smafa_hit rows.  Returns kernels launched;
+// *n_out_host is valid after the stream has been synchronised by the caller (pinned host scalar).
+int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k,
+                    uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out, uint64_t hits_cap,
+                    unsigned long long *n_out_pinned, cudaStream_t s);
+// smafa_hit rows -> candidate keys (for the multi-GPU merge); q must be < 2^20, d < 2^12
+void launch_hits_to_keys(const smafa_hit *hits, uint64_t n, uint64_t *keys, int *bad, cudaStream_t s);
+
+}  // namespace smafa

@@ -1,0 +1,105 @@
+"""Multi-GPU query: the db is row-sharded across ranks (one process per GPU), queries are
+replicated, every rank scans its shard and the per-query local candidates are merged with one
+all-gather of the padded candidate blocks (plus one of the counts) -- SURVEY.md 8e.
+
+Local candidates are a superset of the global answer: Mode A emits the local minimum and its
+ties, Mode B everything <= min(local k-th distance, --max-divergence); the local cutoff is never
+below the global one.  Shards are contiguous row ranges and report global subject indices, so the
+merged (distance, subject) order equals the reference's print order (src/lib.rs:250,307).
+
+torch / torch.distributed are plumbing only (device buffers, streams, NCCL); the scan and the
+merge are the library's own kernels (smafa_query_dev / smafa_merge_dev).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+MAX_SLAB = 1 << 20  # queries per exchange (candidate keys carry 20 query bits)
+
+
+def shard_bounds(D, world_size, rank):
+    """Contiguous row range [lo, hi) of `rank`; the first D % world_size shards get one extra row."""
+    base, extra = divmod(D, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def exchange_candidates(local_rows, group=None):
+    """All-gathers ragged [n_r, 3] int32 candidate blocks; returns the concatenation in rank order.
+    Works on any backend (NCCL on GPUs, gloo in the CPU tests)."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    if ws == 1:
+        return local_rows
+    dev = local_rows.device
+    n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(ws)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    pad = max(max(counts), 1)
+    block = torch.zeros((pad, 3), dtype=torch.int32, device=dev)
+    block[: local_rows.shape[0]] = local_rows
+    blocks = [torch.empty_like(block) for _ in range(ws)]
+    dist.all_gather(blocks, block, group=group)
+    return torch.cat([b[:c] for b, c in zip(blocks, counts)], dim=0)
+
+
+class ShardedSearcher:
+    """Holds this rank's db shard on its GPU and answers replicated query batches."""
+
+    def __init__(self, ctx, db_words, L, world_size=1, rank=0, group=None, hits_capacity=1 << 24, presharded=False):
+        self.ctx, self.L, self.group = ctx, L, group
+        self.world_size, self.rank = world_size, rank
+        self.W = (L + 11) // 12
+        D = db_words.shape[0]
+        if presharded:
+            self.lo = sum_lo = rank * D  # equal shards built rank-locally (bench weak scaling)
+            shard = db_words
+            self.D_total = D * world_size
+        else:
+            self.lo, hi = shard_bounds(D, world_size, rank)
+            shard = db_words[self.lo:hi]
+            self.D_total = D
+        self.db = ctx.upload(np.ascontiguousarray(shard), L, subject_offset=self.lo)
+        self.device = torch.device("cuda", ctx.device)
+        self.hits = torch.empty((hits_capacity, 3), dtype=torch.int32, device=self.device)
+        self.last_stats = None
+
+    def _local(self, q_dev, m, k):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        n, st = self.ctx.query_dev(self.db, q_dev.data_ptr(), q_dev.shape[0], self.L, self.hits.data_ptr(),
+                                   self.hits.shape[0], m, k, stream=stream)
+        self.last_stats = st
+        return self.hits[:n]
+
+    def query_dev(self, q_dev, max_divergence=None, max_num_hits=None):
+        """q_dev: int64 [Q, W] tensor on this rank's GPU (bit pattern of the u64 words).
+        Returns an int32 [n, 3] device tensor of (query, subject, distance) rows in print order,
+        identical on every rank."""
+        out = []
+        launches = 0
+        for s0 in range(0, q_dev.shape[0], MAX_SLAB):
+            slab = q_dev[s0:s0 + MAX_SLAB]
+            rows = self._local(slab, max_divergence, max_num_hits)
+            launches += self.last_stats["kernel_launches"]
+            if self.world_size > 1:
+                union = exchange_candidates(rows, self.group).contiguous()
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                n = self.ctx.merge_dev(union.data_ptr(), union.shape[0], max_divergence, max_num_hits, stream=stream)
+                launches += 8
+                rows = union[:n]
+            rows = rows.clone()
+            if s0:
+                rows[:, 0] += s0
+            out.append(rows)
+        self.last_launches = launches
+        return out[0] if len(out) == 1 else torch.cat(out, dim=0)
+
+    def query_host(self, q_pinned, max_divergence=None, max_num_hits=None):
+        """End-to-end: pinned host words in, host rows out (H2D and D2H inside)."""
+        q_dev = q_pinned.to(self.device, non_blocking=True)
+        rows = self.query_dev(q_dev, max_divergence, max_num_hits)
+        host = rows.cpu()
+        return host.numpy().view(np.uint32)
+
+    def close(self):
+        self.db.close()

@@ -1,0 +1,304 @@
+// Host-side mirror of the reference's public functions: makedb / query / cluster / count
+// (src/lib.rs:137-165, 198-325, 378-398; src/cluster.rs:13-94).  Everything except the distance
+// scan + selection stays on the host exactly as in the reference; the scan goes through the
+// C ABI (smafa_query / smafa_cluster) to the B200 kernels.  There is no CPU fallback for it.
+#include <unistd.h>
+
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/smafa_b200.h"
+#include "../csrc/internal.h"
+#include "seqio.hpp"
+
+using namespace smafa_host;
+
+namespace {
+
+// Rust's `{:?}` of a panic / error maps to: Panic -> exit 101, IoError -> exit 1.
+template <class F>
+int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const Panic &e) {
+    smafa_set_global_error(e.what());
+    return SMAFA_E_PANIC;
+  } catch (const IoError &e) {
+    smafa_set_global_error(e.what());
+    return SMAFA_E_IO;
+  } catch (const std::bad_alloc &) {
+    smafa_set_global_error("out of host memory");
+    return SMAFA_E_OOM;
+  } catch (const std::exception &e) {
+    smafa_set_global_error(e.what());
+    return SMAFA_E_PANIC;
+  }
+}
+
+// Buffered writer to a file descriptor (the reference's println! flushes per line; the bytes are
+// the same).
+struct FdWriter {
+  int fd;
+  std::string buf;
+  explicit FdWriter(int f) : fd(f) { buf.reserve(1 << 20); }
+  void flush() {
+    size_t off = 0;
+    while (off < buf.size()) {
+      ssize_t w = ::write(fd, buf.data() + off, buf.size() - off);
+      if (w <= 0) throw IoError("write failed");
+      off += (size_t)w;
+    }
+    buf.clear();
+  }
+  void maybe_flush() { if (buf.size() >= (1 << 20) - 4096) flush(); }
+  void put_u32(uint32_t v) {
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) buf.push_back(tmp[--n]);
+  }
+};
+
+struct EncodedInput {
+  std::vector<Record> records;
+  std::vector<uint64_t> words;  // [n_ok][W]
+  uint32_t W = 0, L = 0;
+  size_t n_ok = 0;              // records encoded before the first failure
+  bool failed = false;
+  std::string failure;          // panic text of the first bad record
+};
+
+// Encodes records in order until one cannot be handled.  `expect_len` (0 = take the first
+// record's) is the window length every record must have; `mismatch` builds the panic text.
+template <class MismatchMsg>
+EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, MismatchMsg mismatch) {
+  EncodedInput in;
+  in.records = std::move(records);
+  if (in.records.empty()) return in;
+  in.L = expect_len ? expect_len : (uint32_t)in.records[0].seq.size();
+  in.W = words_for_len(in.L);
+  in.words.resize(in.records.size() * (size_t)in.W);
+  for (size_t i = 0; i < in.records.size(); ++i) {
+    const Record &r = in.records[i];
+    std::vector<uint64_t> tmp(words_for_len(r.seq.size()) + 1);
+    try {
+      encode_or_panic(r, tmp.data());  // encoding comes first in the reference (src/lib.rs:150,235)
+    } catch (const Panic &e) {
+      in.failed = true;
+      in.failure = e.what();
+      break;
+    }
+    if (r.seq.size() != in.L) {
+      in.failed = true;
+      in.failure = mismatch(r.seq.size(), in.L);
+      break;
+    }
+    memcpy(in.words.data() + i * in.W, tmp.data(), in.W * sizeof(uint64_t));
+    in.n_ok = i + 1;
+  }
+  return in;
+}
+
+}  // namespace
+
+extern "C" uint8_t smafa_encode_symbol(uint8_t byte) { return SYMBOL_CODE[byte]; }
+
+extern "C" int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos) {
+  if ((!seq && len) || !out_words) return SMAFA_E_INVALID;
+  return encode_window(seq, len, out_words, bad_pos) ? SMAFA_OK : SMAFA_E_PANIC;
+}
+
+extern "C" int smafa_decode_window(const uint64_t *words, size_t len, char *out) {
+  return guarded([&] { decode_window(words, len, out); return (int)SMAFA_OK; });
+}
+
+// src/lib.rs:137-165
+extern "C" int smafa_makedb_file(const char *subject_fasta, const char *db_path) {
+  return guarded([&]() -> int {
+    std::vector<Record> recs = read_fastx(subject_fasta);
+    if (!recs.empty() && recs[0].seq.empty()) {
+      std::vector<uint64_t> t(1);
+      encode_or_panic(recs[0], t.data());
+      throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
+    }
+    EncodedInput in = encode_all(std::move(recs), 0, [](size_t got, uint32_t want) {
+      return "WindowSet seq length is " + std::to_string(want) + ", got a new sequence of length " + std::to_string(got);
+    });
+    if (in.failed) throw Panic(in.failure);
+    WindowDb db;
+    db.n = in.n_ok;
+    db.W = in.W;
+    db.L = in.L;
+    db.words = std::move(in.words);
+    const std::vector<uint8_t> bytes = serialize_db(db);
+    FILE *f = fopen(db_path, "wb");
+    if (!f) throw IoError(std::string("cannot create ") + db_path);
+    const size_t w = fwrite(bytes.data(), 1, bytes.size(), f);
+    fclose(f);
+    if (w != bytes.size()) throw IoError("short write");
+    return SMAFA_OK;
+  });
+}
+
+// src/lib.rs:208-217: File::open(..)? then the version gate
+extern "C" int smafa_db_file_check(const char *db_path) {
+  return guarded([&]() -> int {
+    std::vector<uint8_t> bytes = read_file(db_path);
+    if (bytes.size() > 16) bytes.resize(16);
+    if (bytes.size() < 4) throw Panic("range end index 4 out of range for slice of length " + std::to_string(bytes.size()));
+    uint64_t v = 0;
+    for (int i = 0; i < 4; ++i) {
+      v |= (uint64_t)(bytes[i] & 0x7f) << (7 * i);
+      if (!(bytes[i] & 0x80)) break;
+      if (i == 3) throw IoError("DeserializeUnexpectedEnd");
+    }
+    if (v != DB_VERSION)
+      throw Panic("Unsupported db file version: " + std::to_string(v) + ". This version of smafa only works with version " +
+                  std::to_string(DB_VERSION) + " databases. The last version to support version 1 databases was v0.7.1.");
+    return SMAFA_OK;
+  });
+}
+
+// src/lib.rs:198-325
+extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fasta, int64_t max_divergence,
+                                int64_t max_num_hits, int64_t limit_per_sequence, int out_fd) {
+  smafa_db *dbh = nullptr;
+  int rc = guarded([&]() -> int {
+    if (!ctx) throw Panic("smafa_query_file needs a context (no CPU fallback)");
+    WindowDb db = parse_db(read_file(db_path));  // File::open(..)? -> Err, version gate -> panic
+    std::vector<Record> recs = read_fastx(query_fasta);
+    // get_distances checks the length only when the db is non-empty (src/lib.rs:72)
+    EncodedInput in = encode_all(std::move(recs), db.L, [](size_t got, uint32_t want) {
+      return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
+             std::to_string(want);
+    });
+    const bool mode_b = max_num_hits >= 0 && max_num_hits != 1;  // src/lib.rs:224
+    FdWriter out(out_fd);
+    if (in.n_ok > 0) {
+      int r = smafa_db_upload(ctx, db.words.data(), db.n, db.L, 0, &dbh);
+      if (r) return r;
+      // Mode A with --limit-per-sequence panics right after the first min() (src/lib.rs:298-303)
+      const uint64_t nq = (!mode_b && limit_per_sequence >= 0 && db.n > 0) ? 0 : in.n_ok;
+      smafa_hit *hits = nullptr;
+      uint64_t n_hits = 0;
+      r = smafa_query(ctx, dbh, in.words.data(), nq ? nq : 1, in.L, max_divergence, max_num_hits, &hits, &n_hits, nullptr);
+      if (r) {
+        if (r == SMAFA_E_EMPTY_DB || r == SMAFA_E_BAD_K || r == SMAFA_E_LENGTH_MISMATCH) throw Panic(smafa_last_error(ctx));
+        smafa_set_global_error(smafa_last_error(ctx));
+        return r;
+      }
+      if (nq == 0) {
+        smafa_free(hits);
+        throw Panic("limit_per_sequence is implemented unless max_num_hits > 1. It can be implemented by analogy, "
+                    "just haven't gotten around to it.");
+      }
+      if (mode_b && limit_per_sequence >= 0)
+        n_hits = smafa_apply_limit_per_sequence(hits, n_hits, db.words.data(), db.W, 0, (uint32_t)limit_per_sequence);
+      std::string dec(db.L, '\0');
+      for (uint64_t i = 0; i < n_hits; ++i) {  // src/lib.rs:292,310
+        decode_window(db.words.data() + (size_t)hits[i].subject * db.W, db.L, dec.data());
+        out.put_u32(hits[i].query); out.buf.push_back('\t');
+        out.put_u32(hits[i].subject); out.buf.push_back('\t');
+        out.put_u32(hits[i].distance); out.buf.push_back('\t');
+        out.buf.append(dec); out.buf.push_back('\n');
+        out.maybe_flush();
+      }
+      smafa_free(hits);
+      out.flush();
+    }
+    if (in.failed) throw Panic(in.failure);
+    return SMAFA_OK;
+  });
+  if (dbh) smafa_db_free(dbh);
+  return rc;
+}
+
+// src/cluster.rs:13-94
+extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd) {
+  return guarded([&]() -> int {
+    if (!ctx) throw Panic("smafa_cluster_file needs a context (no CPU fallback)");
+    std::vector<Record> recs = read_fastx(input_fasta);
+    if (!recs.empty() && recs[0].seq.empty()) {
+      std::vector<uint64_t> t(1);
+      encode_or_panic(recs[0], t.data());
+      throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
+    }
+    EncodedInput in = encode_all(std::move(recs), 0, [](size_t got, uint32_t want) {
+      return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
+             std::to_string(want);
+    });
+    // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48)
+    struct Key {
+      const uint64_t *w;
+      uint32_t W;
+      bool operator==(const Key &o) const { return memcmp(w, o.w, W * sizeof(uint64_t)) == 0; }
+    };
+    struct KeyHash {
+      size_t operator()(const Key &k) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint32_t i = 0; i < k.W; ++i) { h ^= k.w[i]; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 31; }
+        return (size_t)h;
+      }
+    };
+    std::unordered_set<Key, KeyHash> seen;
+    seen.reserve(in.n_ok * 2 + 1);
+    std::vector<uint32_t> uniq;  // record index of each unique encoding, input order
+    std::vector<uint64_t> uwords;
+    uwords.reserve(in.n_ok * (size_t)in.W);
+    for (size_t i = 0; i < in.n_ok; ++i) {
+      Key k{in.words.data() + i * in.W, in.W};
+      if (seen.insert(k).second) {
+        uniq.push_back((uint32_t)i);
+        uwords.insert(uwords.end(), k.w, k.w + in.W);
+      }
+    }
+    std::vector<uint32_t> cof(uniq.size());
+    uint64_t n_centroids = 0;
+    if (!uniq.empty()) {
+      int r = smafa_cluster(ctx, uwords.data(), uniq.size(), in.L, max_divergence, cof.data(), &n_centroids, nullptr, nullptr);
+      if (r) { smafa_set_global_error(smafa_last_error(ctx)); return r; }
+    }
+    FdWriter out(out_fd);
+    std::string dec(in.L, '\0');
+    for (size_t u = 0; u < uniq.size(); ++u) {  // src/cluster.rs:79-84: raw input, decoded centroid
+      decode_window(uwords.data() + (size_t)cof[u] * in.W, in.L, dec.data());
+      out.buf.append(in.records[uniq[u]].seq); out.buf.push_back('\t');
+      out.buf.append(dec); out.buf.push_back('\n');
+      out.maybe_flush();
+    }
+    out.flush();
+    if (in.failed) throw Panic(in.failure);
+    return SMAFA_OK;
+  });
+}
+
+// src/lib.rs:378-398
+extern "C" int smafa_count_files(const char *const *paths, size_t n_paths, int out_fd) {
+  return guarded([&]() -> int {
+    std::string js = "[";
+    for (size_t i = 0; i < n_paths; ++i) {
+      std::vector<Record> recs;
+      try {
+        recs = read_fastx(paths[i], /*io_error_on_open=*/true);  // parse_fastx_file(&path)? -> Err
+      } catch (const Panic &e) {
+        throw IoError(e.what());  // count() propagates parse errors with `?`
+      }
+      size_t bases = 0;
+      for (const Record &r : recs) bases += r.seq.size();
+      if (i) js += ',';
+      js += "{\"path\":\"";
+      for (const char *c = paths[i]; *c; ++c) {
+        if (*c == '"' || *c == '\\') js += '\\';
+        js += *c;
+      }
+      js += "\",\"num_reads\":" + std::to_string(recs.size()) + ",\"num_bases\":" + std::to_string(bases) + "}";
+    }
+    js += "]\n";
+    FdWriter out(out_fd);
+    out.buf = js;
+    out.flush();
+    return SMAFA_OK;
+  });
+}

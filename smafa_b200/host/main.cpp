@@ -1,0 +1,115 @@
+// `smafa` command line of the B200 drop-in.  Same subcommands and flags as the reference binary
+// (src/main.rs:64-116); additive flags: --device N, --kernel {auto,popc,mma}.
+// Exit codes follow Rust: 0 ok, 101 for a reference panic, 1 for an Err from main, 2 usage.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smafa_b200.h"
+
+static const char *kVersion = "0.8.0-b200";
+
+static int usage(const std::string &msg) {
+  fprintf(stderr,
+          "error: %s\n\nUsage: smafa [-v|-q] <COMMAND>\n\nCommands:\n"
+          "  makedb   Generate a searchable database            -i <FILE> -d <FILE>\n"
+          "  query    Search a database                         -d <FILE> -q <FILE> [--max-divergence <INT>]\n"
+          "           [--max-num-hits <INT>] [--limit-per-sequence <INT>] [--device <INT>] [--kernel auto|popc|mma]\n"
+          "  cluster  Cluster sequences by similarity           -i <FILE> -d <INT> [--device <INT>] [--kernel ..]\n"
+          "  count    Print the number of reads/bases in a possibly gzipped FASTX file  -i <FILE>...\n",
+          msg.c_str());
+  return 2;
+}
+
+static int finish(int rc, smafa_ctx *ctx) {
+  if (rc == SMAFA_OK) return 0;
+  const char *msg = smafa_last_error(nullptr);
+  if (rc == SMAFA_E_IO) {
+    fprintf(stderr, "Error: %s\n", msg);
+    return 1;
+  }
+  if (rc == SMAFA_E_PANIC) {
+    fprintf(stderr, "thread 'main' panicked:\n%s\n", msg);
+    return 101;
+  }
+  fprintf(stderr, "Error: %s: %s\n", smafa_status_name(rc), ctx ? smafa_last_error(ctx) : msg);
+  return 1;
+}
+
+static bool parse_u32(const char *s, int64_t *out) {
+  char *end = nullptr;
+  unsigned long long v = strtoull(s, &end, 10);
+  if (!*s || *end || s[0] == '-' || v > 0xFFFFFFFFull) return false;
+  *out = (int64_t)v;
+  return true;
+}
+
+int main(int argc, char **argv) {
+  int i = 1;
+  auto is = [&](const char *a, const char *s, const char *l) { return (s && !strcmp(a, s)) || (l && !strcmp(a, l)); };
+  while (i < argc && (is(argv[i], "-v", "--verbose") || is(argv[i], "-q", "--quiet"))) ++i;
+  if (i < argc && is(argv[i], "-V", "--version")) { printf("smafa %s\n", kVersion); return 0; }
+  if (i >= argc) { usage("a subcommand is required"); return 0; }  // reference prints help, exit 0
+  const std::string cmd = argv[i++];
+  const bool is_query = cmd == "query", is_cluster = cmd == "cluster", is_count = cmd == "count", is_makedb = cmd == "makedb";
+  if (!is_query && !is_cluster && !is_count && !is_makedb) return usage("unrecognized subcommand '" + cmd + "'");
+  const char *input = nullptr, *database = nullptr, *query = nullptr;
+  std::vector<const char *> inputs;
+  int64_t m = -1, k = -1, r = -1, device = 0;
+  int kernel = SMAFA_KERNEL_AUTO;
+  for (; i < argc; ++i) {
+    const char *a = argv[i];
+    auto need = [&](int64_t *dst) {
+      if (i + 1 >= argc || !parse_u32(argv[i + 1], dst)) return false;
+      ++i;
+      return true;
+    };
+    if (is(a, "-v", "--verbose") || is(a, nullptr, "--quiet") || (!is_query && is(a, "-q", nullptr))) continue;
+    if (is(a, "-i", "--input") && !is_query) {
+      if (is_count) { while (i + 1 < argc && argv[i + 1][0] != '-') inputs.push_back(argv[++i]); }
+      else if (i + 1 < argc) input = argv[++i];
+      else return usage("a value is required for '--input <FILE>'");
+    } else if (is_cluster && is(a, "-d", "--max-divergence")) { if (!need(&m)) return usage("invalid value for '--max-divergence <INT>'"); }
+    else if ((is_query || is_makedb) && is(a, "-d", "--database") && i + 1 < argc) database = argv[++i];
+    else if (is_query && is(a, "-q", "--query") && i + 1 < argc) query = argv[++i];
+    else if (is_query && is(a, nullptr, "--max-divergence")) { if (!need(&m)) return usage("invalid value for '--max-divergence <INT>'"); }
+    else if (is_query && is(a, nullptr, "--max-num-hits")) { if (!need(&k)) return usage("invalid value for '--max-num-hits <INT>'"); }
+    else if (is_query && is(a, nullptr, "--limit-per-sequence")) { if (!need(&r)) return usage("invalid value for '--limit-per-sequence <INT>'"); }
+    else if ((is_query || is_cluster) && is(a, nullptr, "--device")) { if (!need(&device)) return usage("invalid value for '--device <INT>'"); }
+    else if ((is_query || is_cluster) && is(a, nullptr, "--kernel") && i + 1 < argc) {
+      const std::string v = argv[++i];
+      if (v == "auto") kernel = SMAFA_KERNEL_AUTO;
+      else if (v == "popc") kernel = SMAFA_KERNEL_POPC;
+      else if (v == "mma") kernel = SMAFA_KERNEL_MMA;
+      else return usage("invalid value for '--kernel'");
+    } else return usage(std::string("unexpected argument '") + a + "'");
+  }
+  if (is_makedb) {
+    if (!input || !database) return usage("the following required arguments were not provided: --input <FILE> --database <FILE>");
+    return finish(smafa_makedb_file(input, database), nullptr);
+  }
+  if (is_count) {
+    if (inputs.empty()) return usage("the following required arguments were not provided: --input <FILE>");
+    return finish(smafa_count_files(inputs.data(), inputs.size(), 1), nullptr);
+  }
+  if (is_query && (!database || !query)) return usage("the following required arguments were not provided: --database <FILE> --query <FILE>");
+  if (is_cluster && !input) return usage("the following required arguments were not provided: --input <FILE>");
+  if (is_cluster && m < 0) {  // src/main.rs:43 .unwrap() on the optional -d
+    fprintf(stderr, "thread 'main' panicked:\ncalled `Option::unwrap()` on a `None` value\n");
+    return 101;
+  }
+  if (is_query) {  // open + version gate come first in the reference, before any device work
+    int pre = smafa_db_file_check(database);
+    if (pre) return finish(pre, nullptr);
+  }
+  smafa_ctx *ctx = nullptr;
+  int rc = smafa_ctx_create(&ctx, (int)device, kernel);
+  if (rc) return finish(rc, nullptr);
+  if (is_query) rc = smafa_query_file(ctx, database, query, m, k, r, 1);
+  else rc = smafa_cluster_file(ctx, input, (uint32_t)m, 1);
+  int code = finish(rc, ctx);
+  smafa_ctx_destroy(ctx);
+  return code;
+}

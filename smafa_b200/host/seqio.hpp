@@ -1,0 +1,50 @@
+// Host-side sequence I/O of the B200 smafa drop-in: FASTA/FASTQ(+gz) reading, the 5-bit one-hot
+// window encoding and the db file format.  Stands in for needletail + postcard + the encode /
+// decode helpers of the reference (src/lib.rs:29-52,113-135,137-165,167-196,206-218).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace smafa_host {
+
+// Mirrors a Rust panic! (process exit code 101).
+struct Panic : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+// Mirrors an Err(..) bubbling out of main (exit code 1, "Error: ..." on stderr).
+struct IoError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+constexpr uint32_t DB_VERSION = 2;  // CURRENT_DB_VERSION, src/lib.rs:18
+
+struct Record {
+  std::string id;   // header line without '>' / '@'
+  std::string seq;  // line endings stripped, case preserved
+};
+
+// Whole-file FASTX parse (plain or gzip, sniffed by zlib).  Throws Panic on malformed input
+// (the reference .expect()s needletail's result) and IoError when the file cannot be opened.
+std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open = false);
+
+extern const uint8_t SYMBOL_CODE[256];  // src/lib.rs:167-184; 0 = not a nucleotide
+inline uint32_t words_for_len(size_t len) { return (uint32_t)((len + 11) / 12); }
+// Returns false and sets *bad_pos at the first byte without a code.
+bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_pos);
+void encode_or_panic(const Record &r, uint64_t *out);  // panic text of src/lib.rs:38-41
+void decode_window(const uint64_t *words, size_t len, char *out);  // src/lib.rs:113-135
+
+struct WindowDb {
+  std::vector<uint64_t> words;  // [n][W]
+  uint64_t n = 0;
+  uint32_t W = 0;
+  uint32_t L = 0;  // 0 == None (empty db)
+};
+
+std::vector<uint8_t> serialize_db(const WindowDb &db);  // == postcard::to_allocvec(&WindowSet)
+WindowDb parse_db(const std::vector<uint8_t> &bytes);   // version gate of src/lib.rs:212-217
+std::vector<uint8_t> read_file(const std::string &path);
+
+}  // namespace smafa_host

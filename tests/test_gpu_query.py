@@ -1,0 +1,269 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(libsmafa_b200.so via ctypes) or the `smafa` CLI and is compared bit-exactly with the CPU oracle
+or with the reference's golden vectors."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import smafa_b200
+from oracle import c_oracle
+from smafa_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["popc", "mma"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from smafa_b200 import build
+    build.build()
+    c_oracle.build()
+    c = smafa_b200.Context(0)
+    yield c
+    c.close()
+
+
+def cli(*args):
+    return subprocess.run([api.CLI_PATH, *map(str, args)], capture_output=True, text=True)
+
+
+def check_query(ctx, db, q, L, m, k, r=None, kernel="popc"):
+    ctx.set_kernel(kernel)
+    d = ctx.upload(db, L)
+    try:
+        got, st = ctx.query(d, q, L, max_divergence=m, max_num_hits=k, limit_per_sequence=r, return_stats=True)
+    finally:
+        d.close()
+    want = c_oracle.query(db, L, q, L, m, k, r)
+    assert got.shape == want.shape, (L, m, k, r, kernel, got.shape, want.shape)
+    assert (got == want).all(), (L, m, k, r, kernel)
+    return st
+
+
+# ---- the reference's own golden vectors, through the CLI --------------------------------------
+
+def test_reference_query_kats(ctx, kats, kat_dir, tmp_path):
+    for kernel in KERNELS:
+        for case in kats["query"]:
+            if "makedb_from" in case:
+                db = tmp_path / (case["name"] + ".db")
+                assert cli("makedb", "-i", kat_dir / case["makedb_from"], "-d", db).returncode == 0
+            else:
+                db = kat_dir / case["db"]
+            r = cli("query", "-d", db, "-q", kat_dir / case["query"], "--kernel", kernel, *case["args"])
+            assert r.returncode == 0, (case["name"], r.stderr)
+            assert r.stdout == case["stdout"], (case["name"], kernel)
+
+
+def test_reference_cluster_kats(ctx, kats, kat_dir):
+    for case in kats["cluster"]:
+        r = cli("cluster", "-i", kat_dir / case["input"], "-d", case["t"])
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == case["stdout"], case["name"]
+
+
+def test_cli_panics_match_reference(ctx, kat_dir, tmp_path):
+    db = kat_dir / "random_3_2.fna.smafadb"
+    q = kat_dir / "random_3_2.fna"
+    ragged = tmp_path / "ragged.fna"
+    ragged.write_text(">a\nCTT\n>b\nACGT\n")
+    r = cli("query", "-d", db, "-q", ragged)
+    assert r.returncode == 101
+    assert "Cannot compute distances between seq of length 4 and windows of lengths 3" in r.stderr
+    assert r.stdout == "0\t0\t0\tCTT\n"  # the first record was answered before the panic
+    r = cli("query", "-d", db, "-q", q, "--limit-per-sequence", "1")
+    assert r.returncode == 101 and "limit_per_sequence" in r.stderr
+    r = cli("query", "-d", db, "-q", q, "--max-num-hits", "0")
+    assert r.returncode == 101
+    bad = tmp_path / "bad.fna"
+    bad.write_text(">ok\nCTT\n>x\nCEG\n")
+    r = cli("query", "-d", db, "-q", bad)
+    assert r.returncode == 101 and "Byte 69 cannot be interpreted as nucleotide" in r.stderr
+    assert r.stdout == "0\t0\t0\tCTT\n"
+    r = cli("cluster", "-i", ragged, "-d", "1")
+    assert r.returncode == 101 and r.stdout == "CTT\tCTT\n"
+
+
+def test_cli_full_output_diff_60nt(ctx, tmp_path):
+    # config 1: 1k x 10k 60-nt file, complete stdout diff against the oracle CLI
+    db_sym = synth.make_db(10000, L=60, seed=21)
+    q_sym = synth.make_queries(db_sym, 1000, seed=22)
+    synth.write_fasta(tmp_path / "db.fna", synth.to_ascii(db_sym))
+    synth.write_fasta(tmp_path / "q.fna", synth.to_ascii(q_sym))
+    assert cli("makedb", "-i", tmp_path / "db.fna", "-d", tmp_path / "db").returncode == 0
+    for args in [[], ["--max-divergence", "5"], ["--max-num-hits", "10"],
+                 ["--max-num-hits", "10", "--max-divergence", "7", "--limit-per-sequence", "1"]]:
+        want = subprocess.run([c_oracle.CLI, "query", "-d", tmp_path / "db", "-q", tmp_path / "q.fna", *args],
+                              capture_output=True, text=True)
+        for kernel in KERNELS:
+            got = cli("query", "-d", tmp_path / "db", "-q", tmp_path / "q.fna", "--kernel", kernel, *args)
+            assert got.returncode == 0, got.stderr
+            assert got.stdout == want.stdout, (args, kernel)
+    want = subprocess.run([c_oracle.CLI, "cluster", "-i", tmp_path / "q.fna", "-d", "3"], capture_output=True, text=True)
+    got = cli("cluster", "-i", tmp_path / "q.fna", "-d", "3")
+    assert got.returncode == 0 and got.stdout == want.stdout
+
+
+# ---- get_distances -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L", [1, 3, 4, 6, 9, 12, 13, 20, 32, 33, 60, 61, 64, 65, 100])
+def test_distances_bit_exact(ctx, L):
+    db_sym = synth.make_db(777, L=L, seed=100 + L, family=8, max_subs=min(4, L), noise=0.05)
+    q_sym = synth.make_queries(db_sym, 33, seed=200 + L, max_subs=min(6, L), noise=0.05)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    d = ctx.upload(db, L)
+    got = ctx.distances(d, q, L)
+    d.close()
+    for i in range(q.shape[0]):
+        assert (got[i].astype(np.int64) == c_oracle.distances(db, q[i])).all()
+
+
+# ---- query selection -----------------------------------------------------------------------------
+
+MODES = [(None, None, None), (3, None, None), (0, None, None), (None, 1, None), (None, 2, None), (None, 10, None),
+         (5, 10, None), (2, 50, None), (None, 5000, None), (6, 5000, None), (None, 10, 1), (8, 25, 2), (99, 99, None)]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("L", [1, 3, 9, 12, 20, 32, 33, 60, 63, 64])
+def test_query_matches_oracle(ctx, L, kernel):
+    db_sym = synth.make_db(3000, L=L, seed=300 + L, family=8, max_subs=min(4, L), noise=0.03)
+    q_sym = synth.make_queries(db_sym, 300, seed=400 + L, max_subs=min(6, L), noise=0.03)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    for m, k, r in MODES:
+        check_query(ctx, db, q, L, m, k, r, kernel)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_query_long_windows_generic_path(ctx, kernel):
+    for L in (65, 100, 130):
+        db_sym = synth.make_db(1500, L=L, seed=500 + L)
+        q_sym = synth.make_queries(db_sym, 100, seed=600 + L)
+        db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+        for m, k, r in [(None, None, None), (5, None, None), (None, 7, None), (9, 7, 1)]:
+            check_query(ctx, db, q, L, m, k, r, kernel)
+
+
+def test_query_invalid_codes_fall_back_to_reference_layout(ctx):
+    # a hand-made db may hold words that are not one-hot; the reference just XORs and popcounts
+    rng = np.random.default_rng(5)
+    L = 24
+    db = rng.integers(0, 1 << 60, size=(500, 2), dtype=np.uint64)
+    q = rng.integers(0, 1 << 60, size=(40, 2), dtype=np.uint64)
+    ctx.set_kernel("auto")
+    d = ctx.upload(db, L)
+    got = ctx.query(d, q, L, max_num_hits=5)
+    dist = ctx.distances(d, q, L)
+    d.close()
+    want = c_oracle.query(db, L, q, L, None, 5, None)
+    assert got.shape == want.shape and (got == want).all()
+    assert (dist[0].astype(np.int64) == c_oracle.distances(db, q[0])).all()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ties_duplicates_and_tiny_shapes(ctx, kernel):
+    L = 60
+    one = synth.pack_symbols(synth.random_symbols(1, L, seed=1))
+    same = np.repeat(one, 700, axis=0)  # every window ties
+    q = synth.pack_symbols(synth.random_symbols(5, L, seed=2))
+    q[0] = one[0]
+    for m, k, r in [(None, None, None), (None, 3, None), (None, 3, 2), (None, 800, None), (0, None, None)]:
+        check_query(ctx, same, q, L, m, k, r, kernel)
+    check_query(ctx, one, q, L, None, None, None, kernel)    # D = 1
+    check_query(ctx, one, q, L, None, 2, None, kernel)       # k > D
+    check_query(ctx, same, q[:1], L, None, 10, None, kernel)  # Q = 1
+    ctx.set_kernel(kernel)
+    d = ctx.upload(same, L)
+    assert ctx.query(d, q[:0], L).shape == (0, 3)            # no queries: no output, no panic
+    d.close()
+
+
+def test_reference_panics_through_the_abi(ctx):
+    L = 12
+    db = synth.pack_symbols(synth.random_symbols(10, L, seed=3))
+    q = synth.pack_symbols(synth.random_symbols(2, L, seed=4))
+    d = ctx.upload(db, L)
+    with pytest.raises(smafa_b200.SmafaPanic, match="Cannot compute distances between seq of length 13 and windows of lengths 12"):
+        ctx.query(d, np.zeros((1, 2), dtype=np.uint64), 13)
+    with pytest.raises(smafa_b200.SmafaPanic, match="SMAFA_E_BAD_K"):
+        ctx.query(d, q, L, max_num_hits=0)
+    with pytest.raises(smafa_b200.SmafaPanic, match="limit_per_sequence"):
+        ctx.query(d, q, L, limit_per_sequence=1)
+    d.close()
+    empty = ctx.upload(np.zeros((0, 1), dtype=np.uint64), L)
+    with pytest.raises(smafa_b200.SmafaPanic, match="SMAFA_E_EMPTY_DB"):
+        ctx.query(empty, q, L)
+    with pytest.raises(smafa_b200.SmafaPanic, match="SMAFA_E_EMPTY_DB"):
+        ctx.query(empty, q, L, max_num_hits=3)
+    empty.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_candidate_overflow_retries_are_exact(ctx, kernel):
+    L = 60
+    db_sym = synth.make_db(5000, L=L, seed=31)
+    q_sym = synth.make_queries(db_sym, 700, seed=32)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    ctx.set_candidate_capacity(4096)
+    try:
+        st = check_query(ctx, db, q, L, None, 20, None, kernel)   # floods the buffer -> split batches
+        assert st["retries"] > 0
+        check_query(ctx, db, q, L, None, 6000, None, kernel)      # one query emits D rows > capacity
+    finally:
+        ctx.set_candidate_capacity(0)
+
+
+# ---- cluster -------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("L,t,n", [(60, 3, 20000), (9, 2, 3000), (20, 1, 5000), (60, 0, 2000), (33, 6, 4000)])
+def test_cluster_matches_oracle(ctx, L, t, n, kernel):
+    ctx.set_kernel(kernel)
+    sym = synth.make_cluster_input(n, L=L, seed=700 + L, family=10, max_subs=min(3, L))
+    enc_all = synth.pack_symbols(sym)
+    want_cof, want_nc, want_cmp = c_oracle.cluster(enc_all, L, t)
+    keep = want_cof >= 0  # the host removes duplicate encodings (src/cluster.rs:46-48)
+    enc = enc_all[keep]
+    remap = np.cumsum(keep) - 1
+    cof, nc, ncmp = ctx.cluster(enc, L, t)
+    assert nc == want_nc and ncmp == want_cmp
+    assert (cof.astype(np.int64) == remap[want_cof[keep]]).all()
+
+
+# ---- full-size checks (BASELINE config 2 shape): oracle on a query subsample + properties -------
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config2_scale_subsample_and_properties(ctx, kernel):
+    L, D, Q = 60, 1_000_000, 100_000
+    db_sym = synth.make_db(D, L=L)
+    q_sym = synth.make_queries(db_sym, Q)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    ctx.set_kernel(kernel)
+    d = ctx.upload(db, L)
+    got, st = ctx.query(d, q, L, max_divergence=5, return_stats=True)
+    assert st["pairs"] == Q * D
+    # (1) bit-exact against the oracle on the first 300 queries
+    want = c_oracle.query(db, L, q[:300], L, 5, None, None, threads=os.cpu_count() or 1)
+    sub = got[got[:, 0] < 300]
+    assert sub.shape == want.shape and (sub == want).all()
+    # (2) size-independent properties: sorted print order, distances within the bound, one distance
+    # per query, and every reported distance re-derived from the encodings
+    assert (np.diff(got[:, 0].astype(np.int64)) >= 0).all()
+    assert (got[:, 2] <= 5).all()
+    same_q = got[1:, 0] == got[:-1, 0]
+    assert (got[1:, 2][same_q] == got[:-1, 2][same_q]).all()
+    assert (got[1:, 1][same_q] > got[:-1, 1][same_q]).all()
+    x = np.bitwise_count(db[got[:, 1]] ^ q[got[:, 0]]).sum(axis=1) // 2
+    assert (x == got[:, 2]).all()
+    # (3) self-hit: querying db windows finds them at distance 0 (Mode B, k=3 exercises the k-th path)
+    probe = db[::5000]
+    self_hits = ctx.query(d, probe, L, max_num_hits=3)
+    first = self_hits[np.unique(self_hits[:, 0], return_index=True)[1]]
+    assert (first[:, 2] == 0).all()
+    want = c_oracle.query(db, L, probe[:40], L, None, 3, None, threads=os.cpu_count() or 1)
+    sub = self_hits[self_hits[:, 0] < 40]
+    assert sub.shape == want.shape and (sub == want).all()
+    d.close()
