@@ -171,6 +171,13 @@ uint8_t smafa_encode_symbol(uint8_t byte); /* 0 == not a nucleotide */
 int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos);
 int smafa_decode_window(const uint64_t *words, size_t len, char *out);
 
+/* ---- debug / parity hook --------------------------------------------------------------
+ * Raw int32 accumulators of the tcgen05 formulation for the first 128 db rows x (up to) 256
+ * queries: out[row*256 + col] = matches(row, col) - (L - bound).  Used by the tests to pin the
+ * operand layout and descriptors of the MMA kernel independently of its epilogue. */
+int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q,
+                         uint32_t bound, int32_t *out /* [128][256] */);
+
 #ifdef __cplusplus
 }
 #endif

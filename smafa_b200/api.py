@@ -92,6 +92,7 @@ def load_library():
     l.smafa_cluster_file.argtypes = [vp, C.c_char_p, u32, C.c_int]
     l.smafa_count_files.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, C.c_int]
     l.smafa_db_file_check.argtypes = [C.c_char_p]
+    l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
     l.smafa_encode_symbol.restype = C.c_uint8
     l.smafa_encode_symbol.argtypes = [C.c_uint8]
     l.smafa_encode_window.argtypes = [C.c_char_p, C.c_size_t, vp, C.POINTER(C.c_size_t)]
@@ -214,6 +215,15 @@ class Context:
         if rc:
             _raise(rc, self._h)
         return out.value
+
+    def debug_mma_dump(self, db, q_enc, bound):
+        """Raw tcgen05 accumulators of the first db tile: int32 [128, 256] (see smafa_b200.h)."""
+        q = _words(q_enc)
+        out = np.zeros((128, 256), dtype=np.int32)
+        rc = self._l.smafa_debug_mma_dump(self._h, db.handle, q.ctypes.data, q.shape[0], int(bound), out.ctypes.data)
+        if rc:
+            _raise(rc, self._h)
+        return out
 
     # ---- cluster (reference src/cluster.rs:45-74) on de-duplicated encodings ----
     def cluster(self, enc, L, max_divergence, return_stats=False):

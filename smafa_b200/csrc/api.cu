@@ -382,6 +382,9 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   if (db->generic_only) kernel = -1;
   else if (kernel == SMAFA_KERNEL_AUTO) kernel = mma_supported(db) && ctx->auto_prefers_mma ? SMAFA_KERNEL_MMA : SMAFA_KERNEL_POPC;
   if (kernel == SMAFA_KERNEL_MMA && !mma_supported(db)) kernel = SMAFA_KERNEL_POPC;
+  // a fixed bound that admits everything would send every accumulator down the MMA slow path
+  if (kernel == SMAFA_KERNEL_MMA && plan.mode == MODE_FIXED && plan.bound0 >= (int)db->L) kernel = SMAFA_KERNEL_POPC;
+  ctx->mma_bound0 = plan.bound0;
 
   uint64_t n_cand = 0;
   for (;;) {
@@ -398,7 +401,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       launches += 1;
       p.q_planes = ctx->q_planes;
       if (kernel == SMAFA_KERNEL_MMA) {
-        int l = mma_scan(ctx, db, p, s);
+        int l = mma_scan(ctx, db, p, s, ctx->mma_dump);
         if (l < 0) return l;
         launches += l;
       } else {
@@ -727,4 +730,37 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
   if (n_centroids) *n_centroids = cent_input.size();
   if (n_comparisons) *n_comparisons = comparisons;
   return SMAFA_OK;
+}
+
+// Debug/parity hook for the tcgen05 formulation: runs one MMA scan of (up to 256) queries against the
+// db with a fixed bound and returns the raw int32 accumulators of the first tile
+// (out[row * 256 + col] = matches(db row, query col) - (L - bound)).
+extern "C" int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t bound,
+                                    int32_t *out) {
+  if (!ctx || !db || !q_enc || !out || Q == 0 || Q > 256) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_dump: bad argument");
+  if (!mma_supported(db) || db->D == 0) return fail(ctx, SMAFA_E_UNSUPPORTED, "db not eligible for the MMA kernel");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  int rc;
+  if ((rc = ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, Q * db->W))) return rc;
+  CU(cudaMemcpyAsync(ctx->q_ref, q_enc, Q * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  int32_t *dump = nullptr;
+  CU(cudaMalloc((void **)&dump, 128 * 256 * sizeof(int32_t)));
+  CU(cudaMemsetAsync(dump, 0x7f, 128 * 256 * sizeof(int32_t), s));
+  QueryPlan plan{MODE_FIXED, 0, UINT32_MAX, (int)std::min<uint32_t>(bound, db->L)};
+  const int saved_kernel = ctx->kernel;
+  ctx->kernel = SMAFA_KERNEL_MMA;
+  ctx->mma_dump = dump;
+  uint64_t rows = 0;
+  rc = run_batch(ctx, db, ctx->q_ref, (uint32_t)Q, 0, plan, &rows, s, nullptr);
+  ctx->mma_dump = nullptr;
+  ctx->kernel = saved_kernel;
+  if (rc == SMAFA_OK) {
+    cudaError_t e = cudaMemcpy(out, dump, 128 * 256 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "dump copy: %s", cudaGetErrorString(e));
+  } else if (rc == RC_OVERFLOW) {
+    rc = fail(ctx, SMAFA_E_OOM, "candidate overflow in debug dump");
+  }
+  cudaFree(dump);
+  return rc;
 }

@@ -13,6 +13,8 @@ struct smafa_ctx {
   int kernel = 0;
   int num_sms = 148;
   bool auto_prefers_mma = false;  // set from the measured comparison (profiles/), see DESIGN.md
+  int32_t *mma_dump = nullptr;    // debug hook (smafa_debug_mma_dump)
+  int mma_bound0 = 0;             // initial bound of the batch being scanned (bias of the query operand)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {};
   std::string err;
@@ -57,4 +59,4 @@ int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows);
 int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n);
 void mma_db_free(smafa_db *db);
 // returns kernels launched (>= 0) or a negative smafa_status
-int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s);
+int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s, int32_t *dump = nullptr);

@@ -7,7 +7,7 @@
 //              bit per position:   A=(0,0,0) C=(0,1,0) G=(1,0,0) T=(1,1,0) N/gap=(0,0,1).
 //              Two windows differ at position p  <=>  (H^H')|(Lo^Lo')|(N^N') has bit p set, which
 //              is exactly the reference's "codes differ" rule (N==N is a match, N vs base is a
-//              mismatch).  Row = [H0 Lo0 N0 H1 Lo1 N1 0 0] (32 B, L<=64) or
+//              mismatch).  Row = [H0 Lo0 H1 Lo1 | N0 N1 0 0] (32 B, L<=64) or
 //              [H0 Lo0 N0 0] (16 B, L<=32): one or two aligned 16-byte loads per window.
 //          (2) one-hot int8 rows for the tcgen05 kernel (see scan_mma.cu for the tile layout).
 // Windows holding anything but the five valid codes (possible only in a hand-made db file) set
@@ -46,8 +46,8 @@ __global__ void pack_planes_kernel(const uint64_t *__restrict__ ref, uint32_t n,
   if (bad) atomicOr(invalid, 1);
   uint32_t *row = planes + (size_t)i * row_words;
   if (row_words == 8) {
-    reinterpret_cast<uint4 *>(row)[0] = make_uint4(h[0], lo[0], nn[0], h[1]);
-    reinterpret_cast<uint4 *>(row)[1] = make_uint4(lo[1], nn[1], 0u, 0u);
+    reinterpret_cast<uint4 *>(row)[0] = make_uint4(h[0], lo[0], h[1], lo[1]);
+    reinterpret_cast<uint4 *>(row)[1] = make_uint4(nn[0], nn[1], 0u, 0u);
   } else {
     reinterpret_cast<uint4 *>(row)[0] = make_uint4(h[0], lo[0], nn[0], 0u);
   }

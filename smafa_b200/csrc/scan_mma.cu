@@ -1,9 +1,439 @@
-// Formulation (b): tcgen05 int8 MMA scan -- placeholder until the kernel lands (next commit).
+// Formulation (b): tcgen05 int8 MMA scan (north_star: "matches = one-hot(query) . one-hot(db)^T over
+// 5 symbols x L positions, with the TMEM accumulator drained into the threshold/top-k epilogue").
+// Replaces WindowSet::get_distances + the first selection stage (reference src/lib.rs:71-89,
+// 243-265, 298-312).
+//
+// Operands (int8, K-major, UMMA canonical no-swizzle layout = 8-row x 16-byte core matrices):
+//   K index = symbol * PB + position, symbol in {A,C,G,T,N}, PB = 64 (L <= 63) or 32 (L <= 31)
+//   => K = 320 (10 MMA k-steps of 32) or 160 (5 k-steps).
+//   A = db tile, M = 128 windows (TMEM lanes), streamed: one contiguous 40 KB image per tile in
+//       global memory, fetched with a single cp.async.bulk (TMA bulk copy, no tensor map needed
+//       because pack_onehot_kernel already writes the shared-memory image).
+//   B = query tile, N = 256 queries (TMEM columns), resident in shared memory for a whole work item.
+//   D = A.B^T in TMEM, int32, two 256-column buffers (MMA of tile t+1 overlaps the drain of tile t).
+// Threshold folded into the MMA: the spare K slot (symbol A, position PB-1) holds 1 in every db row
+// and  -need_q  in query q, need_q = L - bound_q, so  D = matches - need_q  and
+//     D >= 0  <=>  distance <= bound_q.
+// The epilogue therefore only ANDs sign bits (one LOP3 per two accumulators); a surviving pair is
+// re-evaluated exactly on the reference words (popcount(a^b)/2) before it is emitted, so the MMA
+// is a conservative filter and bit-exactness never depends on it.  The bias bytes are refreshed from
+// the global bounds every tile by the otherwise idle producer warp (stale = looser = still a
+// superset).
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
+//   warp 0 : bulk-copy producer (B once per item, A tiles through a 3-stage mbarrier ring) + bias refresh
+//   warp 1 : TMEM allocation, single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+//   warps 2-5 : epilogue, one TMEM lane quarter each (tcgen05.ld 32x32b.x32)
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 #include "common.cuh"
 #include "internal.h"
 
-bool mma_supported(const smafa_db *) { return false; }
-int mma_db_reserve(smafa_ctx *, smafa_db *, uint64_t) { return SMAFA_OK; }
-int mma_db_pack(smafa_ctx *, smafa_db *, uint64_t, uint64_t) { return SMAFA_OK; }
-void mma_db_free(smafa_db *db) { cudaFree(db->onehot); db->onehot = nullptr; }
-int mma_scan(smafa_ctx *, const smafa_db *, smafa::ScanParams &, cudaStream_t) { return SMAFA_E_UNSUPPORTED; }
+namespace smafa {
+
+constexpr int MMA_M = 128;      // db windows per tile
+constexpr int MMA_N = 256;      // queries per tile
+constexpr int MMA_STAGES = 3;   // A-tile ring depth
+constexpr int MMA_THREADS = 192;
+
+struct MmaParams {
+  ScanParams sp;
+  const uint8_t *a_tiles;  // [n_db_tiles][128 * KB]
+  const uint8_t *b_tiles;  // [n_qtiles][256 * KB]
+  uint32_t n_qtiles, n_chunks, tiles_per_chunk, n_db_tiles;
+  uint32_t desc_lbo, desc_sbo;  // smem descriptor strides in 16-byte units
+  int need0;                    // initial L - bound (the bias stored in b_tiles)
+  int32_t *dump;                // debug: raw accumulators of work item 0, tile 0 ([128][256]) or nullptr
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_NONE [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
+         (1ull << 46);
+}
+
+// Byte offset of element (row, kbyte) inside a tile image: 8-row groups of KB*8 bytes, inside a
+// group the 16-byte k-chunks are 128 bytes apart and the 8 rows of a chunk are contiguous.
+__host__ __device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t kbyte, uint32_t KB) {
+  return (row >> 3) * (8 * KB) + (kbyte >> 4) * 128 + (row & 7) * 16 + (kbyte & 15);
+}
+
+__device__ __noinline__ void mma_verify_and_emit(const ScanParams *sp, uint32_t q, uint32_t j) {
+  if (q >= sp->Q || j >= sp->d_end) return;
+  int d = ref_distance(sp->q_ref + (size_t)q * sp->W, sp->d_ref + (size_t)j * sp->W, sp->W);
+  int bnd = __ldcg(sp->bound + q);
+  if (d <= bnd) emit_candidate(*sp, q, j, d, bnd);
+}
+
+template <int KSTEPS>
+__global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
+  constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
+  constexpr uint32_t PB = KB / 5;            // positions per symbol block
+  constexpr uint32_t BIAS_K = PB - 1;        // symbol A, position PB-1
+  constexpr uint32_t A_BYTES = MMA_M * KB, B_BYTES = MMA_N * KB;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *sB = smem;
+  uint8_t *sA = smem + B_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BYTES + MMA_STAGES * A_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](uint32_t s) { return bar0 + 8 * s; };
+  auto EMPTY = [&](uint32_t s) { return bar0 + 8 * (3 + s); };
+  auto TFULL = [&](uint32_t b) { return bar0 + 8 * (6 + b); };
+  auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (8 + b); };
+  const uint32_t B_FULL = bar0 + 8 * 10, B_EMPTY = bar0 + 8 * 11, B_READY = bar0 + 8 * 12;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < MMA_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), 4); }
+    mbar_init(B_FULL, 1);
+    mbar_init(B_EMPTY, 1);
+    mbar_init(B_READY, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const ScanParams &sp = P.sp;
+  const uint32_t n_items = P.n_qtiles * P.n_chunks;
+
+  if (warp == 0) {
+    // ===== producer: bulk copies + bias refresh =====
+    uint32_t stage = 0, phase = 0, item_count = 0;
+    int cur[8];
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
+      const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+      const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
+      if (lane == 0) {
+        if (item_count > 0) mbar_wait(B_EMPTY, (item_count - 1) & 1);  // MMAs of the previous item are done with B
+        mbar_expect_tx(B_FULL, B_BYTES);
+        bulk_g2s(smem_u32(sB), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = P.need0;
+      auto refresh = [&]() {
+        bool wrote = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t col = lane * 8 + i, q = qt * MMA_N + col;
+          if (q < sp.Q) {
+            int need = (int)sp.L - __ldcg(sp.bound + q);
+            need = max(0, min(need, 127));
+            if (need != cur[i]) {
+              cur[i] = need;
+              sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-need);
+              wrote = true;
+            }
+          }
+        }
+        if (wrote) fence_proxy_async();  // generic-proxy writes -> visible to the UMMA (async proxy) reads
+        __syncwarp();
+      };
+      mbar_wait(B_FULL, item_count & 1);
+      if (sp.mode != MODE_FIXED) refresh();
+      if (lane == 0) mbar_arrive(B_READY);
+      for (uint32_t t = t_begin; t < t_end; ++t) {
+        if (lane == 0) {
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          mbar_expect_tx(FULL(stage), A_BYTES);
+          bulk_g2s(smem_u32(sA + stage * A_BYTES), P.a_tiles + (size_t)t * A_BYTES, A_BYTES, FULL(stage));
+        }
+        __syncwarp();
+        if (sp.mode != MODE_FIXED) refresh();
+        if (++stage == MMA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32 [4,6)=2, A=S8 [7,10)=1, B=S8 [10,13)=1,
+    // K-major A/B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+    uint32_t stage = 0, phase = 0, tcount = 0, item_count = 0;
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
+      const uint32_t chunk = item / P.n_qtiles;
+      const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
+      mbar_wait(B_READY, item_count & 1);
+      for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
+        const uint32_t buf = tcount & 1, use = tcount >> 1;
+        mbar_wait(TEMPTY(buf), (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        mbar_wait(FULL(stage), phase);          // A tile has landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d_tmem = tmem_base + buf * MMA_N;
+#pragma unroll
+          for (uint32_t ks = 0; ks < (uint32_t)KSTEPS; ++ks) {
+            const uint64_t ad = smem_desc(sA_addr + stage * A_BYTES + ks * 256, P.desc_lbo, P.desc_sbo);
+            const uint64_t bd = smem_desc(sB_addr + ks * 256, P.desc_lbo, P.desc_sbo);
+            tc_mma_i8(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
+          tc_commit(TFULL(buf));    // accumulator ready for the epilogue
+          if (t + 1 == t_end) tc_commit(B_EMPTY);
+        }
+        __syncwarp();
+        if (++stage == MMA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers, sign-AND filter, exact re-check of survivors =====
+    const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    uint32_t tcount = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+      const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
+      const uint32_t qbase = qt * MMA_N;
+      for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
+        const uint32_t buf = tcount & 1, use = tcount >> 1;
+        mbar_wait(TFULL(buf), use & 1);
+        tc_fence_after();
+        const uint32_t row = t * MMA_M + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N;
+#pragma unroll 1
+        for (uint32_t c = 0; c < MMA_N / 32; ++c) {
+          uint32_t v[32];
+          tc_ld32(taddr + c * 32, v);
+          tc_wait_ld();
+          if (P.dump != nullptr && item == 0 && t == t_begin) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) P.dump[(quarter * 32 + lane) * MMA_N + c * 32 + i] = (int32_t)v[i];
+          }
+          uint32_t acc = v[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) acc &= v[i];
+          if ((int)acc >= 0) {  // some accumulator is non-negative: distance <= bound possible
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((int)v[i] >= 0) mma_verify_and_emit(&sp, qbase + c * 32 + i, row);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(TEMPTY(buf));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// One thread per (row, 16-byte k-chunk): writes the int8 one-hot image of rows [row_begin,row_end).
+// Rows >= n_valid are padding: all-zero one-hot and `pad_bias` in the bias slot.
+__global__ void pack_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
+                                   uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, int bias, int pad_bias,
+                                   uint8_t *__restrict__ out) {
+  const uint32_t chunks = KB / 16, PB = KB / 5;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t row = row_begin + (uint32_t)(idx / chunks), c = (uint32_t)(idx % chunks);
+  if (row >= row_end) return;
+  const uint32_t s = (c * 16) / PB, p0 = (c * 16) % PB;
+  const uint32_t want = 16u >> s;  // A C G T N
+  const bool valid = row < n_valid;
+  const uint64_t *w = ref + (size_t)row * W;
+  uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i) {
+    const uint32_t p = p0 + i;
+    uint32_t v = 0;
+    if (valid && p < L) v = (((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u) == want) ? 1u : 0u;
+    if (s == 0 && p == PB - 1) v = (uint32_t)(uint8_t)(int8_t)(valid ? bias : pad_bias);
+    o[i >> 2] |= v << (8 * (i & 3));
+  }
+  const uint32_t tile = row / rows_per_tile, r = row % rows_per_tile;
+  uint8_t *dst = out + (size_t)tile * rows_per_tile * KB + tile_offset(r, c * 16, KB);
+  *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+static void launch_pack_onehot(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
+                               uint32_t L, uint32_t rows_per_tile, uint32_t KB, int bias, int pad_bias, uint8_t *out,
+                               cudaStream_t s) {
+  if (row_end <= row_begin) return;
+  const uint64_t n = (uint64_t)(row_end - row_begin) * (KB / 16);
+  pack_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
+                                                               bias, pad_bias, out);
+}
+
+}  // namespace smafa
+
+using namespace smafa;
+
+static uint32_t mma_kb(const smafa_db *db) { return db->L <= 31 ? 160u : 320u; }
+
+bool mma_supported(const smafa_db *db) { return !db->generic_only && db->L >= 1 && db->L <= 63; }
+
+static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
+  ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+  smafa_set_global_error(ctx->err);
+  return code;
+}
+
+int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
+  if (db->L == 0 || db->L > 63) return SMAFA_OK;
+  const uint64_t tiles = (rows + MMA_M - 1) / MMA_M;
+  if (tiles <= db->onehot_cap) return SMAFA_OK;
+  const size_t tile_bytes = (size_t)MMA_M * mma_kb(db);
+  uint8_t *n = nullptr;
+  cudaError_t e = cudaMalloc((void **)&n, tiles * tile_bytes);
+  if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(one-hot db)", e);
+  if (db->onehot && db->D)
+    cudaMemcpyAsync(n, db->onehot, ((db->D + MMA_M - 1) / MMA_M) * tile_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(db->onehot);
+  db->onehot = n;
+  db->onehot_cap = tiles;
+  return SMAFA_OK;
+}
+
+// Packs rows [first, first+n) and re-pads the tail of the last tile.  db->ref already holds the rows.
+int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
+  if (db->L == 0 || db->L > 63 || n == 0) return SMAFA_OK;
+  const uint32_t end = (uint32_t)(first + n);
+  const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
+  launch_pack_onehot(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), 1, 1, db->onehot, ctx->stream);
+  return SMAFA_OK;
+}
+
+void mma_db_free(smafa_db *db) {
+  cudaFree(db->onehot);
+  db->onehot = nullptr;
+  db->onehot_cap = 0;
+}
+
+int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, int32_t *dump) {
+  const uint32_t KB = mma_kb(db);
+  const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
+  const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB;
+  if (ctx->q_onehot_cap < b_bytes) {
+    cudaStreamSynchronize(s);
+    cudaFree(ctx->q_onehot);
+    ctx->q_onehot = nullptr;
+    ctx->q_onehot_cap = 0;
+    cudaError_t e = cudaMalloc((void **)&ctx->q_onehot, b_bytes);
+    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(one-hot queries)", e);
+    ctx->q_onehot_cap = b_bytes;
+  }
+  // the initial bound is uniform over the batch (launch_init_bound): read it back from the plan via p
+  MmaParams P{};
+  P.sp = p;
+  P.need0 = (int)p.L - ctx->mma_bound0;
+  if (P.need0 < 0) P.need0 = 0;
+  launch_pack_onehot(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, -P.need0, -128, ctx->q_onehot, s);
+  P.dump = dump;
+  P.a_tiles = db->onehot;
+  P.b_tiles = ctx->q_onehot;
+  P.n_qtiles = n_qtiles;
+  P.n_db_tiles = (uint32_t)((db->D + MMA_M - 1) / MMA_M);
+  // work items = query tiles x db chunks; aim at a few hundred items per SM-resident CTA for balance
+  uint32_t tiles_per_chunk = 128;
+  const uint64_t want_items = (uint64_t)ctx->num_sms * 16;
+  while (tiles_per_chunk > 8 && (uint64_t)n_qtiles * ((P.n_db_tiles + tiles_per_chunk - 1) / tiles_per_chunk) < want_items)
+    tiles_per_chunk /= 2;
+  P.tiles_per_chunk = tiles_per_chunk;
+  P.n_chunks = (P.n_db_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  // K-major, no swizzle: LBO = distance between the two 16-byte k-chunks of one k-step (128 B),
+  // SBO = distance between 8-row groups (8*KB bytes)
+  P.desc_lbo = 128 >> 4;
+  P.desc_sbo = (8 * KB) >> 4;
+  if (const char *e = getenv("SMAFA_MMA_SWAP_LBO_SBO")) {
+    if (e[0] == '1') std::swap(P.desc_lbo, P.desc_sbo);
+  }
+  const uint32_t n_items = P.n_qtiles * P.n_chunks;
+  const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, n_items);
+  const size_t smem = (size_t)MMA_N * KB + (size_t)MMA_STAGES * MMA_M * KB + 16 * 8 + 16;
+  cudaError_t e;
+  if (KB == 320) {
+    e = cudaFuncSetAttribute(scan_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "cudaFuncSetAttribute(scan_mma_kernel)", e);
+    scan_mma_kernel<10><<<grid, MMA_THREADS, smem, s>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(scan_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "cudaFuncSetAttribute(scan_mma_kernel)", e);
+    scan_mma_kernel<5><<<grid, MMA_THREADS, smem, s>>>(P);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
+  return 2;
+}

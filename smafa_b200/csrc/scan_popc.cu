@@ -6,9 +6,10 @@
 //    per-query selection state is thread-private, no shared-memory atomics);
 //  * the db is streamed through shared memory in 256-window tiles (one aligned 16/32-byte row per
 //    thread per tile, register-prefetched one tile ahead) and read back as warp-wide broadcasts;
-//  * per pair: 3 LOP3 + 1 POPC per 32 positions, then one compare against the bound;
-//  * EARLY: the second 32 positions are only evaluated when the first 32 already fit the bound
-//    (exact: mismatches only add up) -- halves the POPC count when --max-divergence is small;
+//  * fast path per pair: 2 LOP3 + 1 POPC per 32 positions on the H/Lo planes only (a lower bound of
+//    the distance; the N plane joins in the exact re-check of the rare survivors);
+//  * EARLY: only the first 32 positions are examined by the fast path (mismatches only add up, so
+//    this is again a lower bound) -- one POPC per pair when --max-divergence is small;
 //  * grid = query tiles x db chunks, chunk-major, so co-resident blocks stream the same db chunk
 //    (L2/L1 hits) and later chunks start from bounds tightened by earlier ones.
 #include "common.cuh"
@@ -19,6 +20,7 @@ namespace smafa {
 static constexpr int POPC_THREADS = 256;
 static constexpr int POPC_TILE = 256;  // windows per shared-memory tile
 
+// Row layout (pack.cu): PW=2 -> [H0 Lo0 H1 Lo1 | N0 N1 0 0], PW=1 -> [H0 Lo0 N0 0].
 template <int PW>
 struct Planes {
   uint32_t h[PW], l[PW], n[PW];
@@ -30,7 +32,7 @@ __device__ __forceinline__ Planes<PW> load_row(const uint32_t *__restrict__ base
   if constexpr (PW == 2) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base) + row * 2;
     uint4 a = __ldg(p), b = __ldg(p + 1);
-    r.h[0] = a.x; r.l[0] = a.y; r.n[0] = a.z; r.h[1] = a.w; r.l[1] = b.x; r.n[1] = b.y;
+    r.h[0] = a.x; r.l[0] = a.y; r.h[1] = a.z; r.l[1] = a.w; r.n[0] = b.x; r.n[1] = b.y;
   } else {
     uint4 a = __ldg(reinterpret_cast<const uint4 *>(base) + row);
     r.h[0] = a.x; r.l[0] = a.y; r.n[0] = a.z;
@@ -44,9 +46,15 @@ __device__ __noinline__ int popc_hit(const ScanParams *p, uint32_t q, uint32_t j
   return bound;
 }
 
+// Fast path = a LOWER bound of the distance: the N plane is left out (N is stored as (0,0) in the
+// H/Lo planes), so  popc((H^H')|(Lo^Lo')) <= distance  with equality unless exactly one side has
+// an N at a position where the other has A.  A pair whose lower bound already exceeds the query's
+// bound is rejected with 2 LOP3 + 1 POPC per 32 positions; survivors get the exact 3-plane distance.
 template <int PW, int R, bool EARLY>
-__global__ void __launch_bounds__(POPC_THREADS) scan_popc_kernel(const __grid_constant__ ScanParams p, uint32_t n_qtiles, uint32_t chunk) {
-  constexpr int ROW4 = PW;  // uint4 per row
+__global__ void __launch_bounds__(POPC_THREADS, 3) scan_popc_kernel(const __grid_constant__ ScanParams p, uint32_t n_qtiles, uint32_t chunk) {
+  constexpr int ROW4 = PW;                      // uint4 per row
+  constexpr int FW = (PW == 2 && !EARLY) ? 2 : 1;  // plane words examined by the fast path
+  constexpr int WU = 4;                         // windows per inner iteration
   __shared__ uint4 tile[POPC_TILE * ROW4];
 
   const uint32_t qt = blockIdx.x % n_qtiles, ck = blockIdx.x / n_qtiles;
@@ -71,8 +79,8 @@ __global__ void __launch_bounds__(POPC_THREADS) scan_popc_kernel(const __grid_co
   const uint32_t w_end = min(w_begin + chunk, p.d_end);
   const uint4 *drows = reinterpret_cast<const uint4 *>(p.d_planes);
 
-  // register prefetch of this thread's row of the first tile (the plane matrix is padded to a
-  // multiple of POPC_TILE rows, so the load is always in bounds)
+  // register prefetch of this thread's row of the first tile (the plane matrix is padded by two
+  // tiles of rows, so the load is always in bounds)
   uint4 pre[ROW4];
 #pragma unroll
   for (int v = 0; v < ROW4; ++v) pre[v] = __ldg(drows + (size_t)(w_begin + tid) * ROW4 + v);
@@ -87,50 +95,54 @@ __global__ void __launch_bounds__(POPC_THREADS) scan_popc_kernel(const __grid_co
       for (int v = 0; v < ROW4; ++v) pre[v] = __ldg(drows + (size_t)(t0 + POPC_TILE + tid) * ROW4 + v);
     }
     const int nw = (int)min((uint32_t)POPC_TILE, w_end - t0);
-    // WU windows x R queries per iteration: all POPCs are issued back to back (ILP), one combined
-    // "anything within its bound?" branch per WU*R pairs, and the rare slow path re-checks.
-    constexpr int WU = 2;
+    // WU windows x R queries per iteration: all POPCs are issued back to back (ILP); per query one
+    // min over the WU lower bounds and one compare; one branch per WU*R pairs.
     for (int w = 0; w < nw; w += WU) {
-      uint32_t dh0[WU], dl0[WU], dn0[WU], dh1[WU], dl1[WU], dn1[WU];
+      uint32_t dh[WU][FW], dl[WU][FW];
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        if constexpr (PW == 2) {
+        if constexpr (FW == 2) {
           uint4 a = tile[(w + u) * 2];
-          uint2 b = *reinterpret_cast<const uint2 *>(&tile[(w + u) * 2 + 1]);
-          dh0[u] = a.x; dl0[u] = a.y; dn0[u] = a.z; dh1[u] = a.w; dl1[u] = b.x; dn1[u] = b.y;
+          dh[u][0] = a.x; dl[u][0] = a.y; dh[u][1] = a.z; dl[u][1] = a.w;
         } else {
-          uint4 a = tile[w + u];
-          dh0[u] = a.x; dl0[u] = a.y; dn0[u] = a.z; dh1[u] = dl1[u] = dn1[u] = 0;
+          uint2 a = *reinterpret_cast<const uint2 *>(&tile[(w + u) * ROW4]);
+          dh[u][0] = a.x; dl[u][0] = a.y;
         }
       }
       int c[WU][R];
       bool any = false;
 #pragma unroll
-      for (int u = 0; u < WU; ++u) {
+      for (int r = 0; r < R; ++r) {
+        int mn = 0x7fffffff;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          uint32_t x0 = (q[r].h[0] ^ dh0[u]) | (q[r].l[0] ^ dl0[u]) | (q[r].n[0] ^ dn0[u]);
-          c[u][r] = __popc(x0);
-          if constexpr (PW == 2 && !EARLY) {
-            uint32_t x1 = (q[r].h[1] ^ dh1[u]) | (q[r].l[1] ^ dl1[u]) | (q[r].n[1] ^ dn1[u]);
-            c[u][r] += __popc(x1);
-          }
-          any |= (c[u][r] <= bound[r]);
+        for (int u = 0; u < WU; ++u) {
+          int v = __popc((q[r].h[0] ^ dh[u][0]) | (q[r].l[0] ^ dl[u][0]));
+          if constexpr (FW == 2) v += __popc((q[r].h[1] ^ dh[u][1]) | (q[r].l[1] ^ dl[u][1]));
+          c[u][r] = v;
+          mn = min(mn, v);
         }
+        any |= (mn <= bound[r]);
       }
       if (any) {
 #pragma unroll
         for (int u = 0; u < WU; ++u) {
-          if (w + u < nw) {  // the tile is padded in shared memory, not in the db
+          if (w + u < nw) {  // rows past the chunk end are other windows (or padding): skip
+            Planes<PW> d;
+            if constexpr (PW == 2) {
+              uint4 a = tile[(w + u) * 2], b = tile[(w + u) * 2 + 1];
+              d.h[0] = a.x; d.l[0] = a.y; d.h[1] = a.z; d.l[1] = a.w; d.n[0] = b.x; d.n[1] = b.y;
+            } else {
+              uint4 a = tile[w + u];
+              d.h[0] = a.x; d.l[0] = a.y; d.n[0] = a.z;
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              int d = c[u][r];
-              if (d <= bound[r]) {
-                if constexpr (PW == 2 && EARLY) {
-                  uint32_t x1 = (q[r].h[1] ^ dh1[u]) | (q[r].l[1] ^ dl1[u]) | (q[r].n[1] ^ dn1[u]);
-                  d += __popc(x1);
-                }
-                if (d <= bound[r]) bound[r] = popc_hit(&p, qi[r], t0 + w + u, d, bound[r]);
+              if (c[u][r] <= bound[r]) {
+                int dist = 0;
+#pragma unroll
+                for (int x = 0; x < PW; ++x)
+                  dist += __popc((q[r].h[x] ^ d.h[x]) | (q[r].l[x] ^ d.l[x]) | (q[r].n[x] ^ d.n[x]));
+                if (dist <= bound[r]) bound[r] = popc_hit(&p, qi[r], t0 + w + u, dist, bound[r]);
               }
             }
           }
