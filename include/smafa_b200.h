@@ -177,6 +177,9 @@ int smafa_decode_window(const uint64_t *words, size_t len, char *out);
  * operand layout and descriptors of the MMA kernel independently of its epilogue. */
 int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q,
                          uint32_t bound, int32_t *out /* [128][256] */);
+/* Measured dense int8 tcgen05 rate of this GPU in TOP/s (roofline denominator of the MMA kernel):
+ * every SM issues mmas_per_cta back-to-back M128 x N256 x K32 kind::i8 MMAs on resident operands. */
+int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops);
 
 #ifdef __cplusplus
 }

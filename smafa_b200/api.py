@@ -93,6 +93,7 @@ def load_library():
     l.smafa_count_files.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, C.c_int]
     l.smafa_db_file_check.argtypes = [C.c_char_p]
     l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
+    l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
     l.smafa_encode_symbol.restype = C.c_uint8
     l.smafa_encode_symbol.argtypes = [C.c_uint8]
     l.smafa_encode_window.argtypes = [C.c_char_p, C.c_size_t, vp, C.POINTER(C.c_size_t)]
@@ -215,6 +216,14 @@ class Context:
         if rc:
             _raise(rc, self._h)
         return out.value
+
+    def mma_peak_tops(self, mmas_per_cta=20000):
+        """Measured dense int8 tcgen05 rate of this GPU in TOP/s."""
+        t = C.c_double(0)
+        rc = self._l.smafa_debug_mma_peak(self._h, int(mmas_per_cta), C.byref(t))
+        if rc:
+            _raise(rc, self._h)
+        return t.value
 
     def debug_mma_dump(self, db, q_enc, bound):
         """Raw tcgen05 accumulators of the first db tile: int32 [128, 256] (see smafa_b200.h)."""

@@ -349,8 +349,8 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   int rc;
   uint64_t want_cap = ctx->cand_cap_request ? ctx->cand_cap_request : DEFAULT_CAND_CAP;
   if ((rc = ensure_workspace(ctx, std::max<uint64_t>(want_cap, ctx->ws_cap)))) return rc;
-  if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, Qb))) return rc;
-  launch_init_bound(ctx->bound, Qb, plan.bound0, s);
+  if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, (size_t)Qb + 512))) return rc;  // padded: tile-wide vector loads
+  launch_init_bound(ctx->bound, Qb + 512, plan.bound0, s);
   uint32_t hist_stride = db->L + 1;
   if (plan.mode == MODE_KTH) {
     if ((rc = ensure_buf(ctx, ctx->hist, ctx->hist_cap, (size_t)Qb * hist_stride))) return rc;
@@ -763,4 +763,16 @@ extern "C" int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const ui
   }
   cudaFree(dump);
   return rc;
+}
+
+// Measures the dense int8 tcgen05 rate of this GPU (the roofline denominator of the MMA formulation):
+// every SM issues `mmas_per_cta` back-to-back M128xN256xK32 kind::i8 MMAs on resident operands.
+extern "C" int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops) {
+  if (!ctx || !tops || mmas_per_cta == 0) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_peak: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  float ms = 0;
+  int rc = mma_peak_probe(ctx, mmas_per_cta, &ms);
+  if (rc) return rc;
+  *tops = 2.0 * 128 * 256 * 32 * (double)mmas_per_cta * ctx->num_sms / (ms * 1e-3) / 1e12;
+  return SMAFA_OK;
 }

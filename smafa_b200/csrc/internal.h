@@ -60,3 +60,4 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n);
 void mma_db_free(smafa_db *db);
 // returns kernels launched (>= 0) or a negative smafa_status
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s, int32_t *dump = nullptr);
+int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms);

@@ -20,10 +20,10 @@
 // the global bounds every tile by the otherwise idle producer warp (stale = looser = still a
 // superset).
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
+// Warp roles (320 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
 //   warp 0 : bulk-copy producer (B once per item, A tiles through a 3-stage mbarrier ring) + bias refresh
 //   warp 1 : TMEM allocation, single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-5 : epilogue, one TMEM lane quarter each (tcgen05.ld 32x32b.x32)
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter (128 columns each, tcgen05.ld 32x32b.x32)
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -36,7 +36,8 @@ namespace smafa {
 constexpr int MMA_M = 128;      // db windows per tile
 constexpr int MMA_N = 256;      // queries per tile
 constexpr int MMA_STAGES = 3;   // A-tile ring depth
-constexpr int MMA_THREADS = 192;
+constexpr int MMA_EPI_WARPS = 8;  // two per TMEM lane quarter, each draining half of the columns
+constexpr int MMA_THREADS = 64 + 32 * MMA_EPI_WARPS;
 
 struct MmaParams {
   ScanParams sp;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < MMA_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), 4); }
+    for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
     mbar_init(B_FULL, 1);
     mbar_init(B_EMPTY, 1);
     mbar_init(B_READY, 1);
@@ -189,35 +190,41 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = P.need0;
-      auto refresh = [&]() {
+      // Bias refresh: each lane owns 8 consecutive queries of the tile.  The two 16-byte bound
+      // loads are issued BEFORE the barrier wait so their L2 latency hides behind it (the bound
+      // array is padded to a multiple of the tile width, see run_batch).
+      const int4 *bptr = reinterpret_cast<const int4 *>(sp.bound + (size_t)qt * MMA_N + lane * 8);
+      const bool dyn = sp.mode != MODE_FIXED;
+      auto apply = [&](const int4 &b0, const int4 &b1) {
+        const int bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         bool wrote = false;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t col = lane * 8 + i, q = qt * MMA_N + col;
-          if (q < sp.Q) {
-            int need = (int)sp.L - __ldcg(sp.bound + q);
-            need = max(0, min(need, 127));
-            if (need != cur[i]) {
-              cur[i] = need;
-              sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-need);
-              wrote = true;
-            }
+          const uint32_t col = lane * 8 + i;
+          int need = max(0, min((int)sp.L - bb[i], 127));
+          if (qt * MMA_N + col < sp.Q && need != cur[i]) {
+            cur[i] = need;
+            sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-need);
+            wrote = true;
           }
         }
         if (wrote) fence_proxy_async();  // generic-proxy writes -> visible to the UMMA (async proxy) reads
         __syncwarp();
       };
+      int4 b0 = make_int4(0, 0, 0, 0), b1 = b0;
+      if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
       mbar_wait(B_FULL, item_count & 1);
-      if (sp.mode != MODE_FIXED) refresh();
+      if (dyn) apply(b0, b1);
       if (lane == 0) mbar_arrive(B_READY);
       for (uint32_t t = t_begin; t < t_end; ++t) {
+        if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
         if (lane == 0) {
           mbar_wait(EMPTY(stage), phase ^ 1);
           mbar_expect_tx(FULL(stage), A_BYTES);
           bulk_g2s(smem_u32(sA + stage * A_BYTES), P.a_tiles + (size_t)t * A_BYTES, A_BYTES, FULL(stage));
         }
         __syncwarp();
-        if (sp.mode != MODE_FIXED) refresh();
+        if (dyn) apply(b0, b1);
         if (++stage == MMA_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -255,35 +262,53 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
     }
   } else {
     // ===== epilogue: TMEM -> registers, sign-AND filter, exact re-check of survivors =====
-    const uint32_t quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const uint32_t quarter = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const uint32_t half = (warp - 2) >> 2;      // which 128 of the 256 columns this warp drains
+    constexpr uint32_t CHUNKS = MMA_N / 32 / (MMA_EPI_WARPS / 4);
     uint32_t tcount = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      const uint32_t qbase = qt * MMA_N;
+      const uint32_t qbase = qt * MMA_N + half * (MMA_N / 2);
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(TFULL(buf), use & 1);
         tc_fence_after();
         const uint32_t row = t * MMA_M + quarter * 32 + lane;
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N;
-#pragma unroll 1
-        for (uint32_t c = 0; c < MMA_N / 32; ++c) {
-          uint32_t v[32];
-          tc_ld32(taddr + c * 32, v);
-          tc_wait_ld();
-          if (P.dump != nullptr && item == 0 && t == t_begin) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) P.dump[(quarter * 32 + lane) * MMA_N + c * 32 + i] = (int32_t)v[i];
-          }
-          uint32_t acc = v[0];
-#pragma unroll
-          for (int i = 1; i < 32; ++i) acc &= v[i];
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N + half * (MMA_N / 2);
+        // 32 columns (queries) per TMEM load, software-pipelined: the load of chunk c+1 is in flight
+        // while chunk c is reduced.  The sign-AND is a 4-way tree (one warp per SMSP quarter has no
+        // other warp to hide a serial LOP3 chain behind).
+        auto process = [&](const uint32_t (&v)[32], uint32_t c) {
+          uint32_t a0 = v[0] & v[1] & v[2], a1 = v[8] & v[9] & v[10], a2 = v[16] & v[17] & v[18], a3 = v[24] & v[25] & v[26];
+          a0 &= v[3] & v[4]; a1 &= v[11] & v[12]; a2 &= v[19] & v[20]; a3 &= v[27] & v[28];
+          a0 &= v[5] & v[6]; a1 &= v[13] & v[14]; a2 &= v[21] & v[22]; a3 &= v[29] & v[30];
+          a0 &= v[7] & a1; a2 &= v[15] & a3;
+          const uint32_t acc = a0 & a2 & (v[23] & v[31]);
           if ((int)acc >= 0) {  // some accumulator is non-negative: distance <= bound possible
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if ((int)v[i] >= 0) mma_verify_and_emit(&sp, qbase + c * 32 + i, row);
           }
+        };
+        uint32_t va[32], vb[32];
+        if (P.dump != nullptr && item == 0 && t == t_begin) {  // debug hook, off the hot path
+          for (uint32_t c = 0; c < CHUNKS; ++c) {
+            tc_ld32(taddr + c * 32, va);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) P.dump[(quarter * 32 + lane) * MMA_N + half * (MMA_N / 2) + c * 32 + i] = (int32_t)va[i];
+          }
+        }
+        tc_ld32(taddr, va);
+#pragma unroll 1
+        for (uint32_t c = 0; c < CHUNKS; c += 2) {
+          tc_wait_ld();
+          tc_ld32(taddr + (c + 1) * 32, vb);
+          process(va, c);
+          tc_wait_ld();
+          if (c + 2 < CHUNKS) tc_ld32(taddr + (c + 2) * 32, va);
+          process(vb, c + 1);
         }
         tc_fence_before();
         __syncwarp();
@@ -336,9 +361,60 @@ static void launch_pack_onehot(const uint64_t *ref, uint32_t n_valid, uint32_t r
                                                                bias, pad_bias, out);
 }
 
+// Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten
+// k-step operand offsets like the real kernel); no loads, no epilogue.
+__global__ void __launch_bounds__(64, 1) mma_peak_kernel(uint32_t n_mma) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 128 * 320 + 256 * 320);
+  uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
+  for (uint32_t i = threadIdx.x; i < (128 * 320 + 256 * 320) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 128 * 320;
+    for (uint32_t i = 0; i < n_mma; ++i) {
+      const uint32_t ks = i % 10, buf = (i / 10) & 1;
+      tc_mma_i8(tmem + buf * MMA_N, smem_desc(a0 + ks * 256, 8, 160), smem_desc(b0 + ks * 256, 8, 160), idesc, ks > 0);
+    }
+    tc_commit(smem_u32(bar));
+    mbar_wait(smem_u32(bar), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace smafa
 
 using namespace smafa;
+
+int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms) {
+  const size_t smem = 128 * 320 + 256 * 320 + 64;
+  cudaError_t e = cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SMAFA_E_CUDA; }
+  cudaStream_t s = ctx->stream;
+  mma_peak_kernel<<<ctx->num_sms, 64, smem, s>>>(mmas_per_cta / 10 + 10);  // warm-up
+  cudaEventRecord(ctx->ev[0], s);
+  mma_peak_kernel<<<ctx->num_sms, 64, smem, s>>>(mmas_per_cta);
+  cudaEventRecord(ctx->ev[1], s);
+  e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string("mma_peak_kernel: ") + cudaGetErrorString(e); return SMAFA_E_CUDA; }
+  cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]);
+  return SMAFA_OK;
+}
 
 static uint32_t mma_kb(const smafa_db *db) { return db->L <= 31 ? 160u : 320u; }
 
