@@ -70,10 +70,13 @@ def make_inputs(a, rank, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is
+    started ahead of time (nvidia-smi needs ~0.5 s to come up); only rows whose arrival time falls
+    between mark_begin() and mark_end() are used."""
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -81,7 +84,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,18 +93,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        rows = [r for ts, r in self.rows if len(r) >= 7 and self.t0 <= ts <= self.t1 + 0.03]
+        if not rows:  # region shorter than one sampling period: take the nearest rows
+            rows = [r for ts, r in self.rows if len(r) >= 7][-3:]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [v for v in (num(r[0]) for r in rows) if v is not None]
+        mx = [v for v in (num(r[1]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower() == "active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower() == "active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
@@ -136,28 +155,35 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks):
+def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, int8_peak):
     """Roofline of the dominant (scan) kernel.  This path is compute-bound: operands
     are reused Q x D times, compulsory HBM traffic is a few hundred MB per step."""
     secs = scan_ms / 1e3
     if kernel_used == 2:
         ops = 2 * 5 * L  # int8 ops per comparison: one-hot(query) . one-hot(db)^T over 5 symbols x L
         achieved = pairs_per_launch * ops / secs / 1e12
-        peak = 2.0 * peaks["bf16_tflops_sustained"]  # dense int8 = 2x bf16 on B200 (nominal 4.5 vs 2.25 PF)
-        return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
-                "frac": achieved / peak, "traffic": None,
-                "peak_source": f"2 x {peaks_kind} bf16_tflops_sustained (int8 dense rate = 2 x bf16)",
-                "ops_per_comparison": ops}
+        # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's
+        # issue-only tcgen05 kind::i8 probe (smafa_debug_mma_peak) on this GPU, same clocks.
+        return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
+                "frac": achieved / int8_peak, "traffic": 399.4e6 + 5.6e6,
+                "peak_source": "measured in this run: tcgen05.mma kind::i8 M128xN256xK32 issue-only probe "
+                               f"on all SMs; for reference 2 x {peaks_kind} bf16_tflops = {2 * peaks['bf16_tflops']:.0f}",
+                "ops_per_comparison": ops, "executed_ops_per_comparison": 640,
+                "traffic_source": "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v3_summary.txt (algorithmic: "
+                                  "320 MB one-hot db + 32 MB query tiles)"}
     # POPC formulation: the binding unit is the POPC pipe.  Reference layout = 10 x (XOR32+POPC32)
     # per comparison (5 u64 words, src/lib.rs:85).  The bit-plane packing needs 2 (1 with early exit).
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    popc_peak = 148 * 16 * sm_mhz * 1e6 / 1e12  # 16 POPC lanes/clk/SM
-    achieved = pairs_per_launch * 10 / secs / 1e12
-    return {"bound": "alu", "achieved": achieved, "peak": popc_peak, "unit": "TPOPC/s (reference-layout popcounts)",
-            "frac": achieved / popc_peak, "traffic": None,
-            "peak_source": f"148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (sampled SM clock); the bit-plane packing "
-                           "issues 1-2 POPC per comparison instead of 10, so frac can exceed 1",
-            "ops_per_comparison": 10}
+    popc_peak = 148 * 16 * sm_mhz * 1e6 / 1e12  # XU pipe: 16 POPC lanes/clk/SM (ncu: xu 89-94% busy)
+    popc_per_cmp = 1  # bit-plane fast path with early exit (--max-divergence <= L/4): 1 POPC per pair
+    achieved = pairs_per_launch * popc_per_cmp / secs / 1e12
+    return {"bound": "alu", "achieved": achieved, "peak": popc_peak, "unit": "TPOPC/s",
+            "frac": achieved / popc_peak, "traffic": 35.6e6 + 0.1e6,
+            "peak_source": f"148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (sampled SM clock); the XU (POPC) pipe is the "
+                           "binding unit of the bit-plane formulation (1 POPC + 2 LOP3 per pair); on the reference "
+                           "word layout the same comparison costs 10 POPC",
+            "ops_per_comparison": popc_per_cmp, "reference_layout_popc_per_comparison": 10,
+            "traffic_source": "ncu dram__bytes, profiles/r01_ncu_popc_early_summary.txt"}
 
 
 def run_reference(a):
@@ -222,12 +248,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-input timing (value) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    int8_peak = ctx.mma_peak_tops(50000) if rank == 0 else None
     for _ in range(a.warmup):
         rows = searcher.query_dev(q_dev, MAX_DIVERGENCE, mode_k)
     n_rows = rows.shape[0]
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     scan_ms, launches = 0.0, 0
     t_wall = time.perf_counter()
@@ -240,6 +268,7 @@ def main():
         launches += searcher.last_launches
     barrier()
     t_wall = time.perf_counter() - t_wall
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -265,7 +294,7 @@ def main():
     if rank == 0:
         peaks, peaks_kind = load_peaks()
         st = searcher.last_stats
-        roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks)
+        roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks, int8_peak)
         out = {
             "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,

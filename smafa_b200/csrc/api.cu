@@ -380,7 +380,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
 
   int kernel = ctx->kernel;
   if (db->generic_only) kernel = -1;
-  else if (kernel == SMAFA_KERNEL_AUTO) kernel = mma_supported(db) && ctx->auto_prefers_mma ? SMAFA_KERNEL_MMA : SMAFA_KERNEL_POPC;
+  else if (kernel == SMAFA_KERNEL_AUTO) kernel = mma_supported(db) && ctx->auto_prefers_mma && Qb >= 64 ? SMAFA_KERNEL_MMA : SMAFA_KERNEL_POPC;
   if (kernel == SMAFA_KERNEL_MMA && !mma_supported(db)) kernel = SMAFA_KERNEL_POPC;
   // a fixed bound that admits everything would send every accumulator down the MMA slow path
   if (kernel == SMAFA_KERNEL_MMA && plan.mode == MODE_FIXED && plan.bound0 >= (int)db->L) kernel = SMAFA_KERNEL_POPC;

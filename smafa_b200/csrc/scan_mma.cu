@@ -93,12 +93,24 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// One elected lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on a
+// single thread and emits tcgen05.mma / bulk copies directly instead of a per-active-lane loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+template <bool ACCUMULATE>
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACCUMULATE ? 1 : 0), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
       const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      if (lane == 0) {
+      if (elect_one()) {
         if (item_count > 0) mbar_wait(B_EMPTY, (item_count - 1) & 1);  // MMAs of the previous item are done with B
         mbar_expect_tx(B_FULL, B_BYTES);
         bulk_g2s(smem_u32(sB), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL);
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
       if (lane == 0) mbar_arrive(B_READY);
       for (uint32_t t = t_begin; t < t_end; ++t) {
         if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(EMPTY(stage), phase ^ 1);
           mbar_expect_tx(FULL(stage), A_BYTES);
           bulk_g2s(smem_u32(sA + stage * A_BYTES), P.a_tiles + (size_t)t * A_BYTES, A_BYTES, FULL(stage));
@@ -234,7 +246,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
     // K-major A/B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
     uint32_t stage = 0, phase = 0, tcount = 0, item_count = 0;
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    // descriptors: only the 14-bit start-address field changes (stage and k-step offsets, in 16-byte units)
+    const uint64_t desc_hi = ((uint64_t)(P.desc_lbo & 0x3FFFu) << 16) | ((uint64_t)(P.desc_sbo & 0x3FFFu) << 32) | (1ull << 46);
+    const uint64_t adesc_base = desc_hi | (uint64_t)((smem_u32(sA) >> 4) & 0x3FFFu);
+    const uint64_t bdesc_base = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFFu);
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
       const uint32_t chunk = item / P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
@@ -244,14 +259,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
         mbar_wait(TEMPTY(buf), (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
         mbar_wait(FULL(stage), phase);          // A tile has landed
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t d_tmem = tmem_base + buf * MMA_N;
+          const uint64_t ad = adesc_base + (uint64_t)(stage * (A_BYTES >> 4));
+          tc_mma_i8<false>(d_tmem, ad, bdesc_base, idesc);
 #pragma unroll
-          for (uint32_t ks = 0; ks < (uint32_t)KSTEPS; ++ks) {
-            const uint64_t ad = smem_desc(sA_addr + stage * A_BYTES + ks * 256, P.desc_lbo, P.desc_sbo);
-            const uint64_t bd = smem_desc(sB_addr + ks * 256, P.desc_lbo, P.desc_sbo);
-            tc_mma_i8(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-          }
+          for (uint32_t ks = 1; ks < (uint32_t)KSTEPS; ++ks)
+            tc_mma_i8<true>(d_tmem, ad + ks * 16, bdesc_base + ks * 16, idesc);  // +256 bytes per k-step
           tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
           tc_commit(TFULL(buf));    // accumulator ready for the epilogue
           if (t + 1 == t_end) tc_commit(B_EMPTY);
@@ -378,12 +392,13 @@ __global__ void __launch_bounds__(64, 1) mma_peak_kernel(uint32_t n_mma) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
     const uint32_t a0 = smem_u32(smem), b0 = a0 + 128 * 320;
     for (uint32_t i = 0; i < n_mma; ++i) {
       const uint32_t ks = i % 10, buf = (i / 10) & 1;
-      tc_mma_i8(tmem + buf * MMA_N, smem_desc(a0 + ks * 256, 8, 160), smem_desc(b0 + ks * 256, 8, 160), idesc, ks > 0);
+      if (ks == 0) tc_mma_i8<false>(tmem + buf * MMA_N, smem_desc(a0, 8, 160), smem_desc(b0, 8, 160), idesc);
+      else tc_mma_i8<true>(tmem + buf * MMA_N, smem_desc(a0 + ks * 256, 8, 160), smem_desc(b0 + ks * 256, 8, 160), idesc);
     }
     tc_commit(smem_u32(bar));
     mbar_wait(smem_u32(bar), 0);
