@@ -122,7 +122,9 @@ int smafa_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint6
 /* Same, with queries already in device memory and hits left in a caller-provided device
  * buffer (capacity in rows).  *n_hits receives the number of rows the answer has; when it
  * exceeds hits_capacity the call returns SMAFA_E_OOM and nothing useful is in hits_dev.
- * Work is enqueued on `stream`; the call returns after the stream has been synchronised. */
+ * Work is enqueued on `stream` (NULL = the legacy default stream, as everywhere in CUDA), so it is
+ * ordered after whatever produced q_enc_dev on that stream; the call returns after the stream has
+ * been synchronised. */
 int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc_dev, uint64_t Q,
                     uint32_t q_len, int64_t max_divergence, int64_t max_num_hits,
                     smafa_hit *hits_dev, uint64_t hits_capacity, uint64_t *n_hits,

@@ -534,7 +534,7 @@ extern "C" int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_
   if (rc || Q == 0) return rc;
   if (!q_enc_dev) return fail(ctx, SMAFA_E_INVALID, "smafa_query_dev: null query buffer");
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, like any CUDA API
   cudaEventRecord(ctx->ev[2], s);
   uint64_t total = 0;
   rc = run_range(ctx, db, q_enc_dev, 0, Q, 0, plan, s, stats, [&](uint64_t rows) -> int {
@@ -568,7 +568,7 @@ extern "C" int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n,
   if (!cands_dev) return fail(ctx, SMAFA_E_INVALID, "smafa_merge_dev: null buffer");
   (void)m;  // every shard already applied --max-divergence
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, like any CUDA API
   int rc = ensure_workspace(ctx, std::max<uint64_t>({n, ctx->ws_cap, (uint64_t)1 << 20}));
   if (rc) return rc;
   const bool mode_b = (k >= 0 && k != 1);
