@@ -39,6 +39,7 @@ MAX_DIVERGENCE = 5
 
 
 def parse_args():
+    global MAX_DIVERGENCE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -50,13 +51,16 @@ def parse_args():
     ap.add_argument("--db-per-gpu", type=int, default=D_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    return ap.parse_args()
+    ap.add_argument("--max-divergence", default=str(MAX_DIVERGENCE), help="integer or 'none' (default 5 = configs[1])")
+    a = ap.parse_args()
+    MAX_DIVERGENCE = None if a.max_divergence.lower() == "none" else int(a.max_divergence)
+    return a
 
 
 def workload_name(a, n):
     k = "" if a.mode == "a" else " --max-num-hits 10"
     return (f"synthetic {L}-nt SingleM windows: {a.queries} queries x {a.db_per_gpu * n} db "
-            f"({a.db_per_gpu}/GPU row shard), --max-divergence {MAX_DIVERGENCE}{k}")
+            f"({a.db_per_gpu}/GPU row shard), " + (f"--max-divergence {MAX_DIVERGENCE}" if MAX_DIVERGENCE is not None else "no max-divergence") + k)
 
 
 def make_inputs(a, rank, n):

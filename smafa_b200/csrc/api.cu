@@ -84,6 +84,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   ctx->device = device;
   ctx->kernel = kernel;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("SMAFA_NO_PREPASS")) ctx->disable_prepass = e[0] == '1';
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -351,7 +352,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   if ((rc = ensure_workspace(ctx, std::max<uint64_t>(want_cap, ctx->ws_cap)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, (size_t)Qb + 512))) return rc;  // padded: tile-wide vector loads
   launch_init_bound(ctx->bound, Qb + 512, plan.bound0, s);
-  uint32_t hist_stride = db->L + 1;
+  uint32_t hist_stride = (db->L + 1 + 3) / 4 * 4;  // rows 16-byte aligned for the vector scan in emit_candidate
   if (plan.mode == MODE_KTH) {
     if ((rc = ensure_buf(ctx, ctx->hist, ctx->hist_cap, (size_t)Qb * hist_stride))) return rc;
     CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
@@ -400,6 +401,15 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, ctx->q_planes, q_invalid, s);
       launches += 1;
       p.q_planes = ctx->q_planes;
+      // No useful starting bound (no or a loose --max-divergence): estimate one on a strided db
+      // sample first, otherwise the first tiles of the scan would emit nearly every pair.
+      if (plan.mode != MODE_FIXED && plan.bound0 * 3 > (int)db->L && !ctx->disable_prepass) {
+        const uint32_t n_tiles = (uint32_t)((db->D + 255) / 256);
+        if (n_tiles >= 32) {
+          uint32_t sample_tiles = std::min<uint32_t>(std::max<uint32_t>(n_tiles / 32, 16), 224);
+          launches += launch_bound_prepass(p, std::max<uint32_t>(1, n_tiles / sample_tiles), s);
+        }
+      }
       if (kernel == SMAFA_KERNEL_MMA) {
         int l = mma_scan(ctx, db, p, s, ctx->mma_dump);
         if (l < 0) return l;

@@ -67,17 +67,44 @@ __device__ __forceinline__ void emit_candidate(const ScanParams &p, uint32_t q, 
       atomicMin(p.bound + q, d);
     }
   } else if (p.mode == MODE_KTH) {
+    // hist rows are 16-byte aligned and hist_stride is a multiple of 4 (run_batch)
     uint32_t *h = p.hist + (size_t)q * p.hist_stride;
     atomicAdd(h + d, 1u);
-    uint32_t cum = 0;
-    int nb = bound;
-    for (int t = 0; t <= bound; ++t) {
-      cum += __ldcg(h + t);
-      if (cum >= p.k) { nb = t; break; }
-    }
-    if (nb < bound) {
-      bound = nb;
-      atomicMin(p.bound + q, nb);
+    // Only a candidate strictly below the bound can lower it (the bound drops to t < bound once
+    // #(d <= t) >= k); ties AT the bound -- the common case -- skip the scan.
+    if (d < bound) {
+      uint32_t cum = 0;
+      int nb = bound;
+      const int nvec = (bound + 3) >> 2;  // covers bins [0, bound)
+      const uint4 *hv = reinterpret_cast<const uint4 *>(h);
+      if (nvec <= 16) {
+        // all bins below the bound in ONE round trip: up to 16 independent 16-byte loads are issued
+        // before any of them is consumed
+        uint4 c[16];
+#pragma unroll
+        for (int v = 0; v < 16; ++v) c[v] = v < nvec ? __ldcg(hv + v) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+          const uint32_t cc[4] = {c[v].x, c[v].y, c[v].z, c[v].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int t = v * 4 + j;
+            if (t < bound) {
+              cum += cc[j];
+              if (cum >= p.k && t < nb) nb = t;
+            }
+          }
+        }
+      } else {  // long windows (generic kernel only)
+        for (int t = 0; t < bound; ++t) {
+          cum += __ldcg(h + t);
+          if (cum >= p.k) { nb = t; break; }
+        }
+      }
+      if (nb < bound) {
+        bound = nb;
+        atomicMin(p.bound + q, nb);
+      }
     }
   }
 }

@@ -17,6 +17,8 @@ void launch_init_bound(int *bound, uint32_t Q, int v, cudaStream_t s);
 // scan_popc.cu -- return the number of kernels launched
 int launch_scan_popc(const ScanParams &p, bool early, uint32_t chunk, cudaStream_t s);
 int launch_scan_generic(const ScanParams &p, uint32_t chunk, cudaStream_t s);
+// Bound estimator on every tile_stride-th 256-window tile (no emission); see scan_popc.cu
+int launch_bound_prepass(const ScanParams &p, uint32_t tile_stride, cudaStream_t s);
 void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W,
                       uint16_t *out, cudaStream_t s);
 int popc_tile_rows();

@@ -152,6 +152,79 @@ __global__ void __launch_bounds__(POPC_THREADS, 3) scan_popc_kernel(const __grid
   }
 }
 
+// Bound estimator ("pre-pass"): when a query starts without a useful bound (no --max-divergence),
+// the first tiles of a scan would emit almost every pair.  This kernel scans a strided sample of the
+// db WITHOUT emitting anything and only tightens bound[q]: the minimum distance over the sample
+// (MODE_MIN) or the k-th smallest (MODE_KTH, per-query histogram in shared memory, column-per-thread so
+// no atomics and no bank conflicts).  Any distance seen on a subset of the db is a valid upper bound
+// of the final cutoff, so the main scan (which re-visits the sample) stays exact.
+// One block = 256 queries x the whole sample.
+template <int PW>
+__global__ void __launch_bounds__(POPC_THREADS) bound_prepass_kernel(const __grid_constant__ ScanParams p, uint32_t tile_stride) {
+  constexpr int ROW4 = PW;
+  constexpr int HB = 66;  // bins 0..65 (L <= 64)
+  __shared__ uint4 tile[POPC_TILE * ROW4];
+  extern __shared__ uint16_t hist[];  // [HB][256], MODE_KTH only
+  const uint32_t tid = threadIdx.x, q = blockIdx.x * POPC_THREADS + tid;
+  const bool kth = p.mode == MODE_KTH;
+  Planes<PW> qp{};
+  int best = -1;
+  if (q < p.Q) { qp = load_row<PW>(p.q_planes, q); best = __ldcg(p.bound + q); }
+  if (kth)
+    for (int b = 0; b < HB; ++b) hist[b * POPC_THREADS + tid] = 0;
+  const uint4 *drows = reinterpret_cast<const uint4 *>(p.d_planes);
+  const uint32_t n_tiles = (p.d_end - p.d_begin + POPC_TILE - 1) / POPC_TILE;
+  for (uint32_t t = 0; t < n_tiles; t += tile_stride) {
+    const uint32_t t0 = p.d_begin + t * POPC_TILE;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < ROW4; ++v) tile[tid * ROW4 + v] = __ldg(drows + (size_t)(t0 + tid) * ROW4 + v);
+    __syncthreads();
+    const int nw = (int)min((uint32_t)POPC_TILE, p.d_end - t0);
+    for (int w = 0; w < nw; ++w) {
+      Planes<PW> d;
+      if constexpr (PW == 2) {
+        uint4 a = tile[w * 2], b = tile[w * 2 + 1];
+        d.h[0] = a.x; d.l[0] = a.y; d.h[1] = a.z; d.l[1] = a.w; d.n[0] = b.x; d.n[1] = b.y;
+      } else {
+        uint4 a = tile[w];
+        d.h[0] = a.x; d.l[0] = a.y; d.n[0] = a.z;
+      }
+      int dist = 0;
+#pragma unroll
+      for (int x = 0; x < PW; ++x) dist += __popc((qp.h[x] ^ d.h[x]) | (qp.l[x] ^ d.l[x]) | (qp.n[x] ^ d.n[x]));
+      if (kth) {
+        if (dist <= best) hist[dist * POPC_THREADS + tid]++;  // a sample is < 65536 windows: no overflow
+      } else {
+        best = min(best, dist);
+      }
+    }
+  }
+  if (q >= p.Q) return;
+  if (kth) {
+    uint32_t cum = 0;
+    for (int t = 0; t <= best; ++t) {
+      cum += hist[t * POPC_THREADS + tid];
+      if (cum >= p.k) { best = t; break; }
+    }
+  }
+  atomicMin(p.bound + q, best);
+}
+
+int launch_bound_prepass(const ScanParams &p, uint32_t tile_stride, cudaStream_t s) {
+  if (p.Q == 0 || p.d_end <= p.d_begin || p.L > 64) return 0;
+  const uint32_t blocks = (p.Q + POPC_THREADS - 1) / POPC_THREADS;
+  const size_t smem = p.mode == MODE_KTH ? (size_t)66 * POPC_THREADS * sizeof(uint16_t) : 0;
+  if (p.L <= 32) {
+    if (smem) cudaFuncSetAttribute(bound_prepass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bound_prepass_kernel<1><<<blocks, POPC_THREADS, smem, s>>>(p, tile_stride);
+  } else {
+    if (smem) cudaFuncSetAttribute(bound_prepass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bound_prepass_kernel<2><<<blocks, POPC_THREADS, smem, s>>>(p, tile_stride);
+  }
+  return 1;
+}
+
 // Generic fallback on the reference word layout: any L <= 4095 and arbitrary (even invalid) words,
 // computing popcount(a^b)/2 exactly like src/lib.rs:80-88.  One thread per query.
 __global__ void __launch_bounds__(128) scan_generic_kernel(const ScanParams p, uint32_t n_qtiles, uint32_t chunk) {
