@@ -1,0 +1,15 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 180 python scripts/mma_probe.py > gpurun_out/probe.log 2>&1; P=$?; echo "probe exit=$P" >> gpurun_out/probe.log; tail -6 gpurun_out/probe.log
+SMAFA_MMA_NSYM=5 timeout 180 python scripts/mma_probe.py > gpurun_out/probe5.log 2>&1; echo "probe5 exit=$?" >> gpurun_out/probe5.log; tail -3 gpurun_out/probe5.log
+for NS in 4 5; do for M in "a 5" "a none" "b none"; do set -- $M; SMAFA_MMA_NSYM=$NS timeout 600 python bench.py --kernel mma --mode $1 --max-divergence $2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ns${NS}_$1_$2.json 2> gpurun_out/bench_ns${NS}_$1_$2.err; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_ns${NS}_$1_$2.json").read().strip().splitlines()[-1])
+    print("RESULT nsym=${NS} mode=$1 m=$2 value=%.3e e2e=%.3e ms=%.2f scan_ms=%.2f cands=%d rows=%d"%(d["value"],d["e2e"]["value"],d["ms_per_step"],d["scan_ms_per_step"],d["config"]["candidates_per_step"],d["config"]["hit_rows"]))
+except Exception as e:
+    print("RESULT nsym=${NS} mode=$1 m=$2 FAILED", e); print(open("gpurun_out/bench_ns${NS}_$1_$2.err").read()[-800:])
+PY
+done; done
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest.log; tail -4 gpurun_out/pytest.log

@@ -55,12 +55,19 @@ struct ScanParams {
   uint64_t cand_cap;
 };
 
+// Tightens bound[q] after a candidate at distance d (<= bound) has been recorded.  `bound` is the
+// caller's private copy; the global copy is updated with atomicMin so that blocks working on other
+// db ranges of the same query start from the tightened value.
+__device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, int d, int &bound);
+
 // Slow path shared by all scan kernels: record a candidate and tighten the query's bound.
-// `bound` is the caller's private copy (register); the global copy is updated with atomicMin so
-// that blocks working on other db ranges of the same query start from the tightened value.
 __device__ __forceinline__ void emit_candidate(const ScanParams &p, uint32_t q, uint32_t j, int d, int &bound) {
   unsigned long long slot = atomicAdd(p.cand_count, 1ull);
   if (slot < p.cand_cap) p.cand[slot] = make_key(q, (uint32_t)d, j);
+  tighten_bound(p, q, d, bound);
+}
+
+__device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, int d, int &bound) {
   if (p.mode == MODE_MIN) {
     if (d < bound) {
       bound = d;

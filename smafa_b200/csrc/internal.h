@@ -16,6 +16,7 @@ struct smafa_ctx {
   // B200 at 6.3e12 cmp/s vs 4.3e12 for the POPC kernel with early exit (profiles/r01_*), and its
   // rate does not depend on how tight the bound is.  Tiny query batches stay on the POPC kernel.
   bool auto_prefers_mma = true;
+  uint32_t mma_nsym = 4;          // one-hot symbols per position in the MMA operands (SMAFA_MMA_NSYM=5: ablation)
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
   int32_t *mma_dump = nullptr;    // debug hook (smafa_debug_mma_dump)
   int mma_bound0 = 0;             // initial bound of the batch being scanned (bias of the query operand)
@@ -51,6 +52,7 @@ struct smafa_db {
   int *invalid_flag = nullptr;
   // tcgen05 operand (scan_mma.cu)
   uint8_t *onehot = nullptr;
+  uint32_t mma_nsym = 4;
   uint64_t onehot_cap = 0;
 };
 

@@ -35,7 +35,6 @@ namespace smafa {
 
 constexpr int MMA_M = 128;      // db windows per tile
 constexpr int MMA_N = 256;      // queries per tile
-constexpr int MMA_STAGES = 3;   // A-tile ring depth
 constexpr int MMA_EPI_WARPS = 8;  // two per TMEM lane quarter, each draining half of the columns
 constexpr int MMA_THREADS = 64 + 32 * MMA_EPI_WARPS;
 
@@ -47,6 +46,7 @@ struct MmaParams {
   uint32_t desc_lbo, desc_sbo;  // smem descriptor strides in 16-byte units
   int need0;                    // initial L - bound (the bias stored in b_tiles)
   int32_t *dump;                // debug: raw accumulators of work item 0, tile 0 ([128][256]) or nullptr
+  const uint8_t *q_ncount;      // per query: number of N/gap positions (4-symbol operands), else nullptr
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -140,35 +140,83 @@ __host__ __device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t 
   return (row >> 3) * (8 * KB) + (kbyte >> 4) * 128 + (row & 7) * 16 + (kbyte & 15);
 }
 
-__device__ __noinline__ void mma_verify_and_emit(const ScanParams *sp, uint32_t q, uint32_t j) {
-  if (q >= sp->Q || j >= sp->d_end) return;
-  int d = ref_distance(sp->q_ref + (size_t)q * sp->W, sp->d_ref + (size_t)j * sp->W, sp->W);
-  int bnd = __ldcg(sp->bound + q);
-  if (d <= bnd) emit_candidate(*sp, q, j, d, bnd);
+// Survivors of the sign filter are not verified on the spot (that would serialise up to 32 divergent
+// lanes and stall the TMEM drain): each epilogue warp appends them to a private shared-memory list and
+// drains the list cooperatively -- one survivor per lane, all exact distances in flight together, one
+// global atomicAdd per warp-full of accepted candidates.
+constexpr int MMA_LIST_CAP = 256;  // survivors per epilogue warp between drains
+
+__device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uint32_t j, int &d, int &bnd) {
+  if (q >= sp.Q || j >= sp.d_end) return false;
+  d = ref_distance(sp.q_ref + (size_t)q * sp.W, sp.d_ref + (size_t)j * sp.W, sp.W);
+  bnd = __ldcg(sp.bound + q);
+  return d <= bnd;
 }
 
-template <int KSTEPS>
+// Overflow path (list full): verify and emit immediately.
+__device__ __noinline__ void mma_verify_and_emit(const ScanParams *sp, uint32_t q, uint32_t j) {
+  int d, bnd;
+  if (mma_verify(*sp, q, j, d, bnd)) emit_candidate(*sp, q, j, d, bnd);
+}
+
+__device__ __noinline__ void mma_drain_list(const ScanParams *sp, const uint2 *list, uint32_t n, uint32_t lane) {
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t q = 0, j = 0;
+    int d = 0, bnd = 0;
+    bool ok = false;
+    if (i < n) {
+      const uint2 e = list[i];
+      q = e.x;
+      j = e.y;
+      ok = mma_verify(*sp, q, j, d, bnd);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+    if (mask) {
+      unsigned long long slot0 = 0;
+      if (lane == (uint32_t)(__ffs(mask) - 1)) slot0 = atomicAdd(sp->cand_count, (unsigned long long)__popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(mask) - 1);
+      if (ok) {
+        const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1));
+        if (slot < sp->cand_cap) sp->cand[slot] = make_key(q, (uint32_t)d, j);
+        tighten_bound(*sp, q, d, bnd);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// NSYM = 5: operands hold all five symbols, D = matches - need exactly.
+// NSYM = 4: only A,C,G,T are encoded (K = 256 instead of 320: 20 % less tensor work and operand traffic).
+//           N/gap rows are all-zero, so D counts base-base matches only; because N-N matches are at most
+//           the query's N count nN_q, the bias uses need_q - nN_q and the filter stays conservative:
+//           matches >= need  =>  base matches >= need - nN_q  =>  D >= 0.  Survivors are verified exactly.
+template <int KSTEPS, int NSYM, int STAGES>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
-  constexpr uint32_t PB = KB / 5;            // positions per symbol block
+  constexpr uint32_t PB = KB / NSYM;         // positions per symbol block
   constexpr uint32_t BIAS_K = PB - 1;        // symbol A, position PB-1
   constexpr uint32_t A_BYTES = MMA_M * KB, B_BYTES = MMA_N * KB;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sB = smem;
   uint8_t *sA = smem + B_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BYTES + MMA_STAGES * A_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BYTES + STAGES * A_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  uint32_t *list_count = tmem_slot + 4;                                           // [MMA_EPI_WARPS]
+  uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(bars) + 256);  // [MMA_EPI_WARPS][MMA_LIST_CAP]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
+  static_assert(2 * STAGES + 7 <= 16, "barrier block holds 16 mbarriers");
   auto FULL = [&](uint32_t s) { return bar0 + 8 * s; };
-  auto EMPTY = [&](uint32_t s) { return bar0 + 8 * (3 + s); };
-  auto TFULL = [&](uint32_t b) { return bar0 + 8 * (6 + b); };
-  auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (8 + b); };
-  const uint32_t B_FULL = bar0 + 8 * 10, B_EMPTY = bar0 + 8 * 11, B_READY = bar0 + 8 * 12;
+  auto EMPTY = [&](uint32_t s) { return bar0 + 8 * (STAGES + s); };
+  auto TFULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + b); };
+  auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
+  const uint32_t B_FULL = bar0 + 8 * (2 * STAGES + 4), B_EMPTY = bar0 + 8 * (2 * STAGES + 5), B_READY = bar0 + 8 * (2 * STAGES + 6);
 
+  if (threadIdx.x < MMA_EPI_WARPS) list_count[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < MMA_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
     mbar_init(B_FULL, 1);
     mbar_init(B_EMPTY, 1);
@@ -200,8 +248,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
         bulk_g2s(smem_u32(sB), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL);
       }
       __syncwarp();
+      int nn[8];  // N count of this lane's queries (4-symbol operands only)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = P.need0;
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t q = qt * MMA_N + lane * 8 + i;
+        nn[i] = (NSYM == 4 && q < sp.Q) ? (int)P.q_ncount[q] : 0;
+        cur[i] = max(0, P.need0 - nn[i]);  // what pack_onehot_kernel stored
+      }
       // Bias refresh: each lane owns 8 consecutive queries of the tile.  The two 16-byte bound
       // loads are issued BEFORE the barrier wait so their L2 latency hides behind it (the bound
       // array is padded to a multiple of the tile width, see run_batch).
@@ -213,7 +266,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t col = lane * 8 + i;
-          int need = max(0, min((int)sp.L - bb[i], 127));
+          int need = max(0, min((int)sp.L - bb[i] - nn[i], 127));
           if (qt * MMA_N + col < sp.Q && need != cur[i]) {
             cur[i] = need;
             sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-need);
@@ -237,7 +290,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
         }
         __syncwarp();
         if (dyn) apply(b0, b1);
-        if (++stage == MMA_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -271,7 +324,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
           if (t + 1 == t_end) tc_commit(B_EMPTY);
         }
         __syncwarp();
-        if (++stage == MMA_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -279,6 +332,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
     const uint32_t quarter = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const uint32_t half = (warp - 2) >> 2;      // which 128 of the 256 columns this warp drains
     constexpr uint32_t CHUNKS = MMA_N / 32 / (MMA_EPI_WARPS / 4);
+    uint32_t *my_count = list_count + (warp - 2);
+    uint2 *my_list = lists + (warp - 2) * MMA_LIST_CAP;
     uint32_t tcount = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
@@ -302,7 +357,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
           if ((int)acc >= 0) {  // some accumulator is non-negative: distance <= bound possible
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if ((int)v[i] >= 0) mma_verify_and_emit(&sp, qbase + c * 32 + i, row);
+              if ((int)v[i] >= 0) {
+                const uint32_t slot = atomicAdd(my_count, 1u);
+                if (slot < (uint32_t)MMA_LIST_CAP) my_list[slot] = make_uint2(qbase + c * 32 + i, row);
+                else mma_verify_and_emit(&sp, qbase + c * 32 + i, row);
+              }
           }
         };
         uint32_t va[32], vb[32];
@@ -326,9 +385,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(TEMPTY(buf));
+        if (lane == 0) mbar_arrive(TEMPTY(buf));  // the accumulator buffer is free before any verification starts
+        // Lazy drain: verification is latency-bound (dependent L2 round trips), so survivors are
+        // batched until half the list is full -- 4+ full warp iterations per drain -- and the rest is
+        // flushed once the warp has no tiles left.
+        const uint32_t n_list = min(*my_count, (uint32_t)MMA_LIST_CAP);
+        if (n_list >= (uint32_t)MMA_LIST_CAP / 2) {
+          mma_drain_list(&sp, my_list, n_list, lane);
+          if (lane == 0) *my_count = 0;
+          __syncwarp();
+        }
       }
     }
+    const uint32_t n_left = min(*my_count, (uint32_t)MMA_LIST_CAP);
+    if (n_left) mma_drain_list(&sp, my_list, n_left, lane);
   }
 
   tc_fence_before();
@@ -340,11 +410,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
 }
 
 // One thread per (row, 16-byte k-chunk): writes the int8 one-hot image of rows [row_begin,row_end).
-// Rows >= n_valid are padding: all-zero one-hot and `pad_bias` in the bias slot.
+// Rows >= n_valid are padding: all-zero one-hot and `pad_bias` in the bias slot.  nsym = 4 leaves N/gap
+// positions all-zero; for query rows (ncount != nullptr) the bias becomes -(need0 - nN) and nN is stored.
 __global__ void pack_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
-                                   uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, int bias, int pad_bias,
-                                   uint8_t *__restrict__ out) {
-  const uint32_t chunks = KB / 16, PB = KB / 5;
+                                   uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t nsym, int bias,
+                                   int pad_bias, uint8_t *__restrict__ ncount, uint8_t *__restrict__ out) {
+  const uint32_t chunks = KB / 16, PB = KB / nsym;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t row = row_begin + (uint32_t)(idx / chunks), c = (uint32_t)(idx % chunks);
   if (row >= row_end) return;
@@ -358,7 +429,16 @@ __global__ void pack_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_
     const uint32_t p = p0 + i;
     uint32_t v = 0;
     if (valid && p < L) v = (((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u) == want) ? 1u : 0u;
-    if (s == 0 && p == PB - 1) v = (uint32_t)(uint8_t)(int8_t)(valid ? bias : pad_bias);
+    if (s == 0 && p == PB - 1) {  // the bias slot
+      int bv = valid ? bias : pad_bias;
+      if (valid && ncount != nullptr) {  // query row of the 4-symbol variant
+        int nn = 0;
+        for (uint32_t x = 0; x < L; ++x) nn += (((uint32_t)(w[x / 12] >> (5 * (x % 12))) & 31u) == 1u) ? 1 : 0;
+        ncount[row] = (uint8_t)nn;
+        bv = min(0, bias + nn);  // bias = -need0
+      }
+      v = (uint32_t)(uint8_t)(int8_t)bv;
+    }
     o[i >> 2] |= v << (8 * (i & 3));
   }
   const uint32_t tile = row / rows_per_tile, r = row % rows_per_tile;
@@ -367,12 +447,12 @@ __global__ void pack_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_
 }
 
 static void launch_pack_onehot(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
-                               uint32_t L, uint32_t rows_per_tile, uint32_t KB, int bias, int pad_bias, uint8_t *out,
-                               cudaStream_t s) {
+                               uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t nsym, int bias, int pad_bias,
+                               uint8_t *ncount, uint8_t *out, cudaStream_t s) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)(row_end - row_begin) * (KB / 16);
   pack_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
-                                                               bias, pad_bias, out);
+                                                               nsym, bias, pad_bias, ncount, out);
 }
 
 // Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten
@@ -431,7 +511,7 @@ int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms) {
   return SMAFA_OK;
 }
 
-static uint32_t mma_kb(const smafa_db *db) { return db->L <= 31 ? 160u : 320u; }
+static uint32_t mma_kb(const smafa_db *db) { return (db->L <= 31 ? 32u : 64u) * db->mma_nsym; }
 
 bool mma_supported(const smafa_db *db) { return !db->generic_only && db->L >= 1 && db->L <= 63; }
 
@@ -463,7 +543,8 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   if (db->L == 0 || db->L > 63 || n == 0) return SMAFA_OK;
   const uint32_t end = (uint32_t)(first + n);
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
-  launch_pack_onehot(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), 1, 1, db->onehot, ctx->stream);
+  launch_pack_onehot(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 1, 1, nullptr,
+                     db->onehot, ctx->stream);
   return SMAFA_OK;
 }
 
@@ -473,10 +554,20 @@ void mma_db_free(smafa_db *db) {
   db->onehot_cap = 0;
 }
 
+template <int KSTEPS, int NSYM, int STAGES>
+static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
+  const size_t smem = (size_t)MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 256 +
+                      (size_t)MMA_EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
+  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<KSTEPS, NSYM, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_mma_kernel<KSTEPS, NSYM, STAGES><<<grid, MMA_THREADS, smem, s>>>(P);
+  return cudaGetLastError();
+}
+
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, int32_t *dump) {
   const uint32_t KB = mma_kb(db);
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
-  const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB;
+  const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N;  // operand tiles + N counts
   if (ctx->q_onehot_cap < b_bytes) {
     cudaStreamSynchronize(s);
     cudaFree(ctx->q_onehot);
@@ -486,13 +577,14 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(one-hot queries)", e);
     ctx->q_onehot_cap = b_bytes;
   }
-  // the initial bound is uniform over the batch (launch_init_bound): read it back from the plan via p
+  uint8_t *ncount = db->mma_nsym == 4 ? ctx->q_onehot + (size_t)n_qtiles * MMA_N * KB : nullptr;
   MmaParams P{};
   P.sp = p;
-  P.need0 = (int)p.L - ctx->mma_bound0;
-  if (P.need0 < 0) P.need0 = 0;
-  launch_pack_onehot(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, -P.need0, -128, ctx->q_onehot, s);
+  P.need0 = std::max(0, (int)p.L - ctx->mma_bound0);  // the initial bound is uniform over the batch
+  launch_pack_onehot(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, -P.need0, -128, ncount,
+                     ctx->q_onehot, s);
   P.dump = dump;
+  P.q_ncount = ncount;
   P.a_tiles = db->onehot;
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
@@ -513,18 +605,13 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   }
   const uint32_t n_items = P.n_qtiles * P.n_chunks;
   const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, n_items);
-  const size_t smem = (size_t)MMA_N * KB + (size_t)MMA_STAGES * MMA_M * KB + 16 * 8 + 16;
   cudaError_t e;
-  if (KB == 320) {
-    e = cudaFuncSetAttribute(scan_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "cudaFuncSetAttribute(scan_mma_kernel)", e);
-    scan_mma_kernel<10><<<grid, MMA_THREADS, smem, s>>>(P);
-  } else {
-    e = cudaFuncSetAttribute(scan_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "cudaFuncSetAttribute(scan_mma_kernel)", e);
-    scan_mma_kernel<5><<<grid, MMA_THREADS, smem, s>>>(P);
+  switch (KB) {
+    case 320: e = launch_mma<10, 5, 3>(P, grid, s); break;
+    case 160: e = launch_mma<5, 5, 3>(P, grid, s); break;
+    case 256: e = launch_mma<8, 4, 4>(P, grid, s); break;
+    default: e = launch_mma<4, 4, 4>(P, grid, s); break;  // 128
   }
-  e = cudaGetLastError();
   if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
   return 2;
 }

@@ -121,6 +121,34 @@ def test_distances_bit_exact(ctx, L):
         assert (got[i].astype(np.int64) == c_oracle.distances(db, q[i])).all()
 
 
+# ---- raw tcgen05 accumulators (pins operand layout + descriptors independently of the epilogue) ----
+
+@pytest.mark.parametrize("nsym", [4, 5])
+@pytest.mark.parametrize("L", [20, 60])
+def test_mma_accumulators_exact(L, nsym, monkeypatch):
+    monkeypatch.setenv("SMAFA_MMA_NSYM", str(nsym))
+    c = smafa_b200.Context(0, "mma")
+    try:
+        db_sym = synth.make_db(1000, L=L, seed=1, noise=0.05)
+        q_sym = synth.make_queries(db_sym, 256, seed=2, noise=0.05)
+        d = c.upload(synth.pack_symbols(db_sym), L)
+        bound = 7
+        acc = c.debug_mma_dump(d, synth.pack_symbols(q_sym), bound)
+        eq = db_sym[:128, None, :] == q_sym[None, :, :]
+        if nsym == 5:   # D = matches - need
+            want = eq.sum(axis=2) - (L - bound)
+        else:           # D = base-base matches - (need - nN_q)
+            want = (eq & (q_sym[None, :, :] < 4)).sum(axis=2) - np.maximum(0, (L - bound) - (q_sym == 4).sum(axis=1))[None, :]
+        assert (acc == want.astype(np.int32)).all()
+        # and the 5-symbol variant still answers queries exactly
+        got = c.query(d, synth.pack_symbols(q_sym), L, max_divergence=9, max_num_hits=5)
+        want_rows = c_oracle.query(synth.pack_symbols(db_sym), L, synth.pack_symbols(q_sym), L, 9, 5, None)
+        assert got.shape == want_rows.shape and (got == want_rows).all()
+        d.close()
+    finally:
+        c.close()
+
+
 # ---- query selection -----------------------------------------------------------------------------
 
 MODES = [(None, None, None), (3, None, None), (0, None, None), (None, 1, None), (None, 2, None), (None, 10, None),
