@@ -85,7 +85,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   ctx->kernel = kernel;
   ctx->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("SMAFA_NO_PREPASS")) ctx->disable_prepass = e[0] == '1';
-  if (const char *e = getenv("SMAFA_MMA_NSYM")) ctx->mma_nsym = e[0] == '5' ? 5 : 4;
+  if (const char *e = getenv("SMAFA_MMA_NSYM")) ctx->mma_nsym = (e[0] >= '2' && e[0] <= '5') ? (uint32_t)(e[0] - '0') : 3;
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -232,7 +232,7 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
   db->row_words = row_words_for(L);
   db->generic_only = (db->row_words == 0);
   db->subject_offset = subject_offset;
-  db->mma_nsym = ctx->mma_nsym;
+  db->mma_nsym = mma_pick_encoding(ctx->mma_nsym, L);
   cudaError_t e = cudaMalloc((void **)&db->invalid_flag, sizeof(int));
   if (e != cudaSuccess) { delete db; return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(db->invalid_flag, 0, sizeof(int), ctx->stream);

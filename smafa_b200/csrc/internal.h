@@ -16,7 +16,7 @@ struct smafa_ctx {
   // B200 at 6.3e12 cmp/s vs 4.3e12 for the POPC kernel with early exit (profiles/r01_*), and its
   // rate does not depend on how tight the bound is.  Tiny query batches stay on the POPC kernel.
   bool auto_prefers_mma = true;
-  uint32_t mma_nsym = 4;          // one-hot symbols per position in the MMA operands (SMAFA_MMA_NSYM=5: ablation)
+  uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
   int32_t *mma_dump = nullptr;    // debug hook (smafa_debug_mma_dump)
   int mma_bound0 = 0;             // initial bound of the batch being scanned (bias of the query operand)
@@ -52,7 +52,7 @@ struct smafa_db {
   int *invalid_flag = nullptr;
   // tcgen05 operand (scan_mma.cu)
   uint8_t *onehot = nullptr;
-  uint32_t mma_nsym = 4;
+  uint32_t mma_nsym = 3;      // encoding of `onehot` (mma_pick_encoding)
   uint64_t onehot_cap = 0;
 };
 
@@ -61,6 +61,7 @@ void smafa_set_global_error(const std::string &s);
 
 // scan_mma.cu
 bool mma_supported(const smafa_db *db);
+uint32_t mma_pick_encoding(uint32_t want, uint32_t L);
 int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows);
 int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n);
 void mma_db_free(smafa_db *db);

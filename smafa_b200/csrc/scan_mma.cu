@@ -35,8 +35,9 @@ namespace smafa {
 
 constexpr int MMA_M = 128;      // db windows per tile
 constexpr int MMA_N = 256;      // queries per tile
-constexpr int MMA_EPI_WARPS = 8;  // two per TMEM lane quarter, each draining half of the columns
-constexpr int MMA_THREADS = 64 + 32 * MMA_EPI_WARPS;
+// Epilogue warps: EPI_WARPS/4 per TMEM lane quarter (a warp may only read the 32 lanes of quarter warp%4),
+// each draining MMA_N / (EPI_WARPS/4) accumulator columns of every tile.
+constexpr int mma_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 
 struct MmaParams {
   ScanParams sp;
@@ -46,8 +47,33 @@ struct MmaParams {
   uint32_t desc_lbo, desc_sbo;  // smem descriptor strides in 16-byte units
   int need0;                    // initial L - bound (the bias stored in b_tiles)
   int32_t *dump;                // debug: raw accumulators of work item 0, tile 0 ([128][256]) or nullptr
-  const uint8_t *q_ncount;      // per query: number of N/gap positions (4-symbol operands), else nullptr
+  const int16_t *q_meta;        // per query: N/gap count (ENC 4) or bias base (ENC 2/3, see HadCoef), else nullptr
 };
+
+// ---- operand encodings ------------------------------------------------------------------------
+// ENC = 5 : one-hot over A,C,G,T,N           K = 5*PB   D = matches - need                    (exact threshold)
+// ENC = 4 : one-hot over A,C,G,T             K = 4*PB   D = base matches - (need - nN_q)      (conservative)
+// ENC = 3 : +-1 character features (h, l, h*l) of the 2-bit base code, N/gap = (0,0,0)
+//           K = 3*PB.  Per position with two bases  h*h' + l*l' + hl*hl' = 4*[match] - 1,  so with
+//           S = feature dot product, n_bb = #positions where both are bases = L - nN_q - nN_d + nNN:
+//               4*matches = S + (L - nN_q - nN_d) + 5*nNN            (nNN = positions where both are N)
+// ENC = 2 : features (h, l) only, K = 2*PB.  h*h' + l*l' is 2 / 0 / 0 / -2, so [match] <= (u + 2)/4 and
+//               4*matches <= S + 2*(L - nN_q - nN_d) + 6*nNN         (lossy but conservative)
+// For ENC 2/3 the spare K slots (positions >= L of each feature block) carry the rest of the inequality
+//     D = S + c_q - alpha*nN_d + (alpha+4)*min'(nN_q, nN_d) >= 0,   c_q = alpha*(L - nN_q) - 4*need_q
+//   spare 0,1 : db 1,            query c_q split into two int8 (refreshed as bound_q tightens)
+//   spare 2   : db -alpha*nN_d,  query 1
+//   spare 3+t : thermometer code of the N counts, t < T: db [nN_d >= t+1], query (alpha+4)*[nN_q >= t+1];
+//               the last level carries (alpha+4)*max(0, nN_q-(T-1)) so the sum is >= min(nN_q, nN_d) >= nNN.
+// Every variant is a conservative filter; survivors are re-evaluated exactly before they are emitted.
+__host__ __device__ __forceinline__ uint32_t mma_pb(uint32_t enc, uint32_t L) { return L <= (enc <= 3 ? 30u : 31u) ? 32u : 64u; }
+__host__ __device__ __forceinline__ bool mma_enc_ok(uint32_t enc, uint32_t L) { return L >= 1 && L <= (enc <= 3 ? 62u : 63u); }
+// k index of spare slot si (feature-block major)
+__host__ __device__ __forceinline__ uint32_t had_spare_k(uint32_t si, uint32_t PB, uint32_t L) {
+  const uint32_t gap = PB - L;
+  return (si / gap) * PB + L + si % gap;
+}
+__host__ __device__ __forceinline__ int clamp8(int v) { return v < -128 ? -128 : (v > 127 ? 127 : v); }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 
@@ -125,6 +151,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// Same shape with .pack::16b: register i = low 16 bits of column 2i | low 16 bits of column 2i+1 << 16, i.e.
+// 64 accumulator columns per load.  |D| < 2^15 for every encoding, so bit 15 is still the sign.
+__device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
@@ -143,7 +183,8 @@ __host__ __device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t 
 // Survivors of the sign filter are not verified on the spot (that would serialise up to 32 divergent
 // lanes and stall the TMEM drain): each epilogue warp appends them to a private shared-memory list and
 // drains the list cooperatively -- one survivor per lane, all exact distances in flight together, one
-// global atomicAdd per warp-full of accepted candidates.
+// global atomicAdd per warp-full of accepted candidates.  Everything here is inlined: a call inside the
+// epilogue loop makes ptxas keep loop state in local memory (seen in the v5 SASS).
 constexpr int MMA_LIST_CAP = 256;  // survivors per epilogue warp between drains
 
 __device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uint32_t j, int &d, int &bnd) {
@@ -153,37 +194,49 @@ __device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uin
   return d <= bnd;
 }
 
-// Overflow path (list full): verify and emit immediately.
-__device__ __noinline__ void mma_verify_and_emit(const ScanParams *sp, uint32_t q, uint32_t j) {
-  int d, bnd;
-  if (mma_verify(*sp, q, j, d, bnd)) emit_candidate(*sp, q, j, d, bnd);
-}
-
-__device__ __noinline__ void mma_drain_list(const ScanParams *sp, const uint2 *list, uint32_t n, uint32_t lane) {
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    uint32_t q = 0, j = 0;
-    int d = 0, bnd = 0;
-    bool ok = false;
-    if (i < n) {
-      const uint2 e = list[i];
-      q = e.x;
-      j = e.y;
-      ok = mma_verify(*sp, q, j, d, bnd);
-    }
-    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    if (mask) {
-      unsigned long long slot0 = 0;
-      if (lane == (uint32_t)(__ffs(mask) - 1)) slot0 = atomicAdd(sp->cand_count, (unsigned long long)__popc(mask));
-      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(mask) - 1);
-      if (ok) {
-        const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1));
-        if (slot < sp->cand_cap) sp->cand[slot] = make_key(q, (uint32_t)d, j);
-        tighten_bound(*sp, q, d, bnd);
-      }
+// Warp-converged: verifies 32 (q, j) pairs at a time (lane-private pair, `have` = lane holds one).
+__device__ __forceinline__ void mma_verify_emit_warp(const ScanParams &sp, bool have, uint32_t q, uint32_t j, uint32_t lane) {
+  int d = 0, bnd = 0;
+  const bool ok = have && mma_verify(sp, q, j, d, bnd);
+  const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+  if (mask) {
+    const int leader = __ffs(mask) - 1;
+    unsigned long long slot0 = 0;
+    if ((int)lane == leader) slot0 = atomicAdd(sp.cand_count, (unsigned long long)__popc(mask));
+    slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+    if (ok) {
+      const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1));
+      if (slot < sp.cand_cap) sp.cand[slot] = make_key(q, (uint32_t)d, j);
+      tighten_bound(sp, q, d, bnd);
     }
   }
+}
+
+__device__ __forceinline__ void mma_drain_list(const ScanParams &sp, const uint2 *list, uint32_t n, uint32_t lane) {
+#pragma unroll 1
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    uint2 e = make_uint2(0, 0);
+    if (i < n) e = list[i];
+    mma_verify_emit_warp(sp, i < n, e.x, e.y, lane);
+  }
   __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;  // opaque to the optimiser: keeps the reduction a tree instead of one dependent LOP3 chain
+  asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// AND of 32 registers, depth 4
+__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
+  uint32_t t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = and3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  t[10] = v[30] & v[31];
+  const uint32_t u0 = and3(t[0], t[1], t[2]), u1 = and3(t[3], t[4], t[5]), u2 = and3(t[6], t[7], t[8]);
+  const uint32_t u3 = t[9] & t[10];
+  return and3(u0, u1, u2) & u3;
 }
 
 // NSYM = 5: operands hold all five symbols, D = matches - need exactly.
@@ -191,18 +244,19 @@ __device__ __noinline__ void mma_drain_list(const ScanParams *sp, const uint2 *l
 //           N/gap rows are all-zero, so D counts base-base matches only; because N-N matches are at most
 //           the query's N count nN_q, the bias uses need_q - nN_q and the filter stays conservative:
 //           matches >= need  =>  base matches >= need - nN_q  =>  D >= 0.  Survivors are verified exactly.
-template <int KSTEPS, int NSYM, int STAGES>
-__global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16>
+__global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
+  constexpr int MMA_EPI_WARPS = EPI_WARPS;
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
-  constexpr uint32_t PB = KB / NSYM;         // positions per symbol block
-  constexpr uint32_t BIAS_K = PB - 1;        // symbol A, position PB-1
+  constexpr uint32_t PB = KB / NSYM;         // positions per symbol / feature block
+  constexpr uint32_t BIAS_K = PB - 1;        // one-hot encodings: symbol A, position PB-1
+  constexpr bool HAD = NSYM <= 3;            // +-1 feature encodings: bias in spare slots 0 and 1
   constexpr uint32_t A_BYTES = MMA_M * KB, B_BYTES = MMA_N * KB;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sB = smem;
   uint8_t *sA = smem + B_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BYTES + STAGES * A_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-  uint32_t *list_count = tmem_slot + 4;                                           // [MMA_EPI_WARPS]
   uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(bars) + 256);  // [MMA_EPI_WARPS][MMA_LIST_CAP]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,7 +268,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
   auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
   const uint32_t B_FULL = bar0 + 8 * (2 * STAGES + 4), B_EMPTY = bar0 + 8 * (2 * STAGES + 5), B_READY = bar0 + 8 * (2 * STAGES + 6);
 
-  if (threadIdx.x < MMA_EPI_WARPS) list_count[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
@@ -248,12 +301,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
         bulk_g2s(smem_u32(sB), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL);
       }
       __syncwarp();
-      int nn[8];  // N count of this lane's queries (4-symbol operands only)
+      int meta[8];  // per-query constant of this lane's queries (see MmaParams::q_meta)
+      // bias value of a query at bound b: one-hot = need (stored negated), +-1 features = c_q
+      auto bias_of = [&](int m, int b) -> int {
+        const int need = max(0, min((int)sp.L - b, (int)sp.L));
+        if constexpr (HAD) return min(254, m - 4 * need);
+        else return max(0, min(need - m, 127));
+      };
+      const uint32_t k0 = had_spare_k(0, PB, sp.L), k1 = had_spare_k(1, PB, sp.L);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t q = qt * MMA_N + lane * 8 + i;
-        nn[i] = (NSYM == 4 && q < sp.Q) ? (int)P.q_ncount[q] : 0;
-        cur[i] = max(0, P.need0 - nn[i]);  // what pack_onehot_kernel stored
+        meta[i] = (NSYM != 5 && q < sp.Q) ? (int)P.q_meta[q] : 0;
+        cur[i] = bias_of(meta[i], (int)sp.L - P.need0);  // what pack_operand_kernel stored
       }
       // Bias refresh: each lane owns 8 consecutive queries of the tile.  The two 16-byte bound
       // loads are issued BEFORE the barrier wait so their L2 latency hides behind it (the bound
@@ -266,10 +326,18 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t col = lane * 8 + i;
-          int need = max(0, min((int)sp.L - bb[i] - nn[i], 127));
-          if (qt * MMA_N + col < sp.Q && need != cur[i]) {
-            cur[i] = need;
-            sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-need);
+          const int v = bias_of(meta[i], bb[i]);
+          if (qt * MMA_N + col < sp.Q && v != cur[i]) {
+            cur[i] = v;
+            if constexpr (HAD) {
+              // both halves are monotone in c, so a reader that sees one old and one new byte still
+              // sees a value between the old and the new c: looser, never tighter
+              const int c0 = clamp8(v);
+              sB[tile_offset(col, k0, KB)] = (uint8_t)(int8_t)c0;
+              sB[tile_offset(col, k1, KB)] = (uint8_t)(int8_t)(v - c0);
+            } else {
+              sB[tile_offset(col, BIAS_K, KB)] = (uint8_t)(int8_t)(-v);
+            }
             wrote = true;
           }
         }
@@ -330,75 +398,137 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
   } else {
     // ===== epilogue: TMEM -> registers, sign-AND filter, exact re-check of survivors =====
     const uint32_t quarter = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const uint32_t half = (warp - 2) >> 2;      // which 128 of the 256 columns this warp drains
-    constexpr uint32_t CHUNKS = MMA_N / 32 / (MMA_EPI_WARPS / 4);
-    uint32_t *my_count = list_count + (warp - 2);
+    const uint32_t part = (warp - 2) >> 2;      // which column range of the tile this warp drains
+    constexpr uint32_t COLS_PER_WARP = MMA_N / (MMA_EPI_WARPS / 4);
+    constexpr uint32_t COLS_PER_LD = PACK16 ? 64 : 32;
+    constexpr uint32_t CHUNKS = COLS_PER_WARP / COLS_PER_LD;
     uint2 *my_list = lists + (warp - 2) * MMA_LIST_CAP;
+    uint32_t count = 0;  // entries in my_list (warp-uniform)
     uint32_t tcount = 0;
+    // Slow path, entered by the whole warp when any lane saw a non-negative accumulator in chunk c:
+    // per-lane survivor bit masks, a warp scan for the list offsets, then a short per-lane store loop.
+    auto slow = [&](const uint32_t (&v)[32], uint32_t qc, uint32_t row) {
+      uint32_t m0 = 0, m1 = 0;  // bit i: accumulator i (pack16: low / high half of register i) is >= 0
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if constexpr (PACK16) {
+          m0 |= ((~v[i] >> 15) & 1u) << i;
+          m1 |= (~v[i] >> 31) << i;
+        } else {
+          m0 |= (~v[i] >> 31) << i;
+        }
+      }
+      const uint32_t n = __popc(m0) + __popc(m1);
+      uint32_t incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += y;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      if (count + total > (uint32_t)MMA_LIST_CAP) {
+        mma_drain_list(sp, my_list, count, lane);
+        count = 0;
+      }
+      if (total > (uint32_t)MMA_LIST_CAP) {
+        // a flood (bound admits > 1/4 of the chunk): verify straight from the masks, warp-wide per bit
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i) {
+          mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row, lane);
+          if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row, lane);
+        }
+      } else {
+        uint32_t off = count + incl - n;
+        while (m0) {
+          const int i = __ffs(m0) - 1;
+          m0 &= m0 - 1;
+          my_list[off++] = make_uint2(qc + (PACK16 ? 2 * i : i), row);
+        }
+        if constexpr (PACK16) {
+          while (m1) {
+            const int i = __ffs(m1) - 1;
+            m1 &= m1 - 1;
+            my_list[off++] = make_uint2(qc + 2 * i + 1, row);
+          }
+        }
+        count += total;
+      }
+      __syncwarp();
+    };
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      const uint32_t qbase = qt * MMA_N + half * (MMA_N / 2);
+      const uint32_t qbase = qt * MMA_N + part * COLS_PER_WARP;
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(TFULL(buf), use & 1);
         tc_fence_after();
         const uint32_t row = t * MMA_M + quarter * 32 + lane;
-        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N + half * (MMA_N / 2);
-        // 32 columns (queries) per TMEM load, software-pipelined: the load of chunk c+1 is in flight
-        // while chunk c is reduced.  The sign-AND is a 4-way tree (one warp per SMSP quarter has no
-        // other warp to hide a serial LOP3 chain behind).
-        auto process = [&](const uint32_t (&v)[32], uint32_t c) {
-          uint32_t a0 = v[0] & v[1] & v[2], a1 = v[8] & v[9] & v[10], a2 = v[16] & v[17] & v[18], a3 = v[24] & v[25] & v[26];
-          a0 &= v[3] & v[4]; a1 &= v[11] & v[12]; a2 &= v[19] & v[20]; a3 &= v[27] & v[28];
-          a0 &= v[5] & v[6]; a1 &= v[13] & v[14]; a2 &= v[21] & v[22]; a3 &= v[29] & v[30];
-          a0 &= v[7] & a1; a2 &= v[15] & a3;
-          const uint32_t acc = a0 & a2 & (v[23] & v[31]);
-          if ((int)acc >= 0) {  // some accumulator is non-negative: distance <= bound possible
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if ((int)v[i] >= 0) {
-                const uint32_t slot = atomicAdd(my_count, 1u);
-                if (slot < (uint32_t)MMA_LIST_CAP) my_list[slot] = make_uint2(qbase + c * 32 + i, row);
-                else mma_verify_and_emit(&sp, qbase + c * 32 + i, row);
-              }
-          }
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N + part * COLS_PER_WARP;
+        auto load = [&](uint32_t c, uint32_t (&v)[32]) {
+          if constexpr (PACK16) tc_ld32_pack16(taddr + c * 64, v);
+          else tc_ld32(taddr + c * 32, v);
         };
-        uint32_t va[32], vb[32];
+        auto process = [&](const uint32_t (&v)[32], uint32_t c) {
+          const uint32_t acc = and_tree32(v);
+          const bool hit = PACK16 ? (acc & 0x80008000u) != 0x80008000u : (int)acc >= 0;
+          if (__any_sync(0xffffffffu, hit)) slow(v, qbase + c * COLS_PER_LD, row);
+        };
+        uint32_t va[32];
         if (P.dump != nullptr && item == 0 && t == t_begin) {  // debug hook, off the hot path
           for (uint32_t c = 0; c < CHUNKS; ++c) {
-            tc_ld32(taddr + c * 32, va);
+            load(c, va);
             tc_wait_ld();
+            int32_t *drow = P.dump + (quarter * 32 + lane) * MMA_N + part * COLS_PER_WARP + c * COLS_PER_LD;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) P.dump[(quarter * 32 + lane) * MMA_N + half * (MMA_N / 2) + c * 32 + i] = (int32_t)va[i];
+            for (int i = 0; i < 32; ++i) {
+              if constexpr (PACK16) {
+                drow[2 * i] = (int32_t)(int16_t)(va[i] & 0xffffu);
+                drow[2 * i + 1] = (int32_t)(int16_t)(va[i] >> 16);
+              } else {
+                drow[i] = (int32_t)va[i];
+              }
+            }
           }
         }
-        tc_ld32(taddr, va);
-#pragma unroll 1
-        for (uint32_t c = 0; c < CHUNKS; c += 2) {
+        if constexpr (CHUNKS == 1) {
+          // the whole column range fits one load: the accumulator buffer is released as soon as the
+          // registers hold it, before any filtering
+          load(0, va);
           tc_wait_ld();
-          tc_ld32(taddr + (c + 1) * 32, vb);
-          process(va, c);
-          tc_wait_ld();
-          if (c + 2 < CHUNKS) tc_ld32(taddr + (c + 2) * 32, va);
-          process(vb, c + 1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(TEMPTY(buf));
+          process(va, 0);
+        } else {
+          // two loads in flight; the buffer is released after the last wait
+          uint32_t vb[32];
+          load(0, va);
+#pragma unroll
+          for (uint32_t c = 0; c < CHUNKS; c += 2) {
+            load(c + 1, vb);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 2 == CHUNKS) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(TEMPTY(buf));
+            }
+            process(va, c);
+            if (c + 2 < CHUNKS) load(c + 2, va);
+            process(vb, c + 1);
+            if (c + 2 < CHUNKS) tc_wait_ld();
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(TEMPTY(buf));  // the accumulator buffer is free before any verification starts
         // Lazy drain: verification is latency-bound (dependent L2 round trips), so survivors are
         // batched until half the list is full -- 4+ full warp iterations per drain -- and the rest is
         // flushed once the warp has no tiles left.
-        const uint32_t n_list = min(*my_count, (uint32_t)MMA_LIST_CAP);
-        if (n_list >= (uint32_t)MMA_LIST_CAP / 2) {
-          mma_drain_list(&sp, my_list, n_list, lane);
-          if (lane == 0) *my_count = 0;
-          __syncwarp();
+        if (count >= (uint32_t)MMA_LIST_CAP / 2) {
+          mma_drain_list(sp, my_list, count, lane);
+          count = 0;
         }
       }
     }
-    const uint32_t n_left = min(*my_count, (uint32_t)MMA_LIST_CAP);
-    if (n_left) mma_drain_list(&sp, my_list, n_left, lane);
+    if (count) mma_drain_list(sp, my_list, count, lane);
   }
 
   tc_fence_before();
@@ -409,50 +539,76 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const __grid_c
   }
 }
 
-// One thread per (row, 16-byte k-chunk): writes the int8 one-hot image of rows [row_begin,row_end).
-// Rows >= n_valid are padding: all-zero one-hot and `pad_bias` in the bias slot.  nsym = 4 leaves N/gap
-// positions all-zero; for query rows (ncount != nullptr) the bias becomes -(need0 - nN) and nN is stored.
-__global__ void pack_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
-                                   uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t nsym, int bias,
-                                   int pad_bias, uint8_t *__restrict__ ncount, uint8_t *__restrict__ out) {
-  const uint32_t chunks = KB / 16, PB = KB / nsym;
+// One thread per (row, 16-byte k-chunk): writes the int8 operand image of rows [row_begin,row_end) in
+// encoding `enc` (see "operand encodings" above).  Rows >= n_valid are padding and can never pass the
+// sign filter.  Query rows (is_query) get their bias for the batch's initial need0 = L - bound0 and
+// their per-query constant in meta[].
+__global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
+                                    uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query,
+                                    int need0, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
+  const uint32_t chunks = KB / 16, PB = KB / enc, gap = PB - L;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t row = row_begin + (uint32_t)(idx / chunks), c = (uint32_t)(idx % chunks);
   if (row >= row_end) return;
-  const uint32_t s = (c * 16) / PB, p0 = (c * 16) % PB;
-  const uint32_t want = 16u >> s;  // A C G T N
-  const bool valid = row < n_valid;
+  const bool valid = row < n_valid, had = enc <= 3;
   const uint64_t *w = ref + (size_t)row * W;
+  int nN = 0;  // N/gap positions: code 1 = bit 0 of a 5-bit group
+  if (valid)
+    for (uint32_t i = 0; i < W; ++i) nN += __popcll(w[i] & 0x0084210842108421ull);
+  const int alpha = enc == 2 ? 2 : 1, w5 = alpha + 4, T = (int)(enc * gap) - 3;
+  const int over = max(0, nN - (T - 1));
+  int qbase = 0, cq = 0;
+  if (had) {
+    qbase = alpha * ((int)L - nN) + max(0, w5 * over - 127);
+    cq = min(254, qbase - 4 * need0);
+  }
   uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
   for (uint32_t i = 0; i < 16; ++i) {
-    const uint32_t p = p0 + i;
-    uint32_t v = 0;
-    if (valid && p < L) v = (((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u) == want) ? 1u : 0u;
-    if (s == 0 && p == PB - 1) {  // the bias slot
-      int bv = valid ? bias : pad_bias;
-      if (valid && ncount != nullptr) {  // query row of the 4-symbol variant
-        int nn = 0;
-        for (uint32_t x = 0; x < L; ++x) nn += (((uint32_t)(w[x / 12] >> (5 * (x % 12))) & 31u) == 1u) ? 1 : 0;
-        ncount[row] = (uint8_t)nn;
-        bv = min(0, bias + nn);  // bias = -need0
+    const uint32_t k = c * 16 + i, f = k / PB, p = k % PB;
+    int v = 0;
+    if (p < L) {
+      if (valid) {
+        const uint32_t code = (uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u;
+        if (!had) {
+          v = code == (16u >> f);  // A C G T N
+        } else if (code >= 2 && (code & (code - 1)) == 0) {
+          // A=16 (+,+,+)  C=8 (+,-,-)  G=4 (-,+,-)  T=2 (-,-,+): h, l, h*l
+          const uint32_t plus = f == 0 ? (16u | 8u) : (f == 1 ? (16u | 4u) : (16u | 2u));
+          v = (code & plus) ? 1 : -1;
+        }
       }
-      v = (uint32_t)(uint8_t)(int8_t)bv;
+    } else if (!had) {
+      if (f == 0 && p == PB - 1)  // the bias slot
+        v = !is_query ? 1 : (valid ? -max(0, min(need0 - (enc == 4 ? nN : 0), 127)) : -128);
+    } else {
+      const int si = (int)(f * gap + (p - L));
+      if (is_query) {
+        if (si == 0) v = valid ? clamp8(cq) : -128;
+        else if (si == 1) v = valid ? cq - clamp8(cq) : -128;
+        else if (si == 2) v = 1;
+        else if (valid) v = (si - 3) < T - 1 ? (nN >= si - 2 ? w5 : 0) : min(127, w5 * over);
+      } else {
+        if (si <= 1) v = 1;
+        else if (si == 2) v = valid ? -alpha * nN : -128;
+        else v = (valid && nN >= si - 2) ? 1 : 0;
+      }
     }
-    o[i >> 2] |= v << (8 * (i & 3));
+    o[i >> 2] |= ((uint32_t)v & 0xffu) << (8 * (i & 3));
   }
+  if (is_query && meta != nullptr && c == 0) meta[row] = (int16_t)(valid ? (had ? qbase : nN) : 0);
   const uint32_t tile = row / rows_per_tile, r = row % rows_per_tile;
   uint8_t *dst = out + (size_t)tile * rows_per_tile * KB + tile_offset(r, c * 16, KB);
   *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-static void launch_pack_onehot(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
-                               uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t nsym, int bias, int pad_bias,
-                               uint8_t *ncount, uint8_t *out, cudaStream_t s) {
+static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
+                                uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query, int need0,
+                                int16_t *meta, uint8_t *out, cudaStream_t s) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)(row_end - row_begin) * (KB / 16);
-  pack_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
-                                                               nsym, bias, pad_bias, ncount, out);
+  pack_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
+                                                                enc, is_query, need0, meta, out);
 }
 
 // Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten
@@ -511,9 +667,16 @@ int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms) {
   return SMAFA_OK;
 }
 
-static uint32_t mma_kb(const smafa_db *db) { return (db->L <= 31 ? 32u : 64u) * db->mma_nsym; }
+static uint32_t mma_kb(const smafa_db *db) { return mma_pb(db->mma_nsym, db->L) * db->mma_nsym; }
 
-bool mma_supported(const smafa_db *db) { return !db->generic_only && db->L >= 1 && db->L <= 63; }
+// The encoding a db of window length L gets when `want` is requested (+-1 features need two spare
+// positions per feature block: L = 63 falls back to the 4-symbol one-hot operands).
+uint32_t mma_pick_encoding(uint32_t want, uint32_t L) {
+  if (want < 2 || want > 5) want = 3;
+  return mma_enc_ok(want, L) ? want : 4;
+}
+
+bool mma_supported(const smafa_db *db) { return !db->generic_only && mma_enc_ok(db->mma_nsym, db->L); }
 
 static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
   ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -543,8 +706,8 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   if (db->L == 0 || db->L > 63 || n == 0) return SMAFA_OK;
   const uint32_t end = (uint32_t)(first + n);
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
-  launch_pack_onehot(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 1, 1, nullptr,
-                     db->onehot, ctx->stream);
+  launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0, nullptr,
+                      db->onehot, ctx->stream);
   return SMAFA_OK;
 }
 
@@ -554,20 +717,21 @@ void mma_db_free(smafa_db *db) {
   db->onehot_cap = 0;
 }
 
-template <int KSTEPS, int NSYM, int STAGES>
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16>
 static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
   const size_t smem = (size_t)MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 256 +
-                      (size_t)MMA_EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<KSTEPS, NSYM, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                      (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
+  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scan_mma_kernel<KSTEPS, NSYM, STAGES><<<grid, MMA_THREADS, smem, s>>>(P);
+  kern<<<grid, mma_threads(EPI_WARPS), smem, s>>>(P);
   return cudaGetLastError();
 }
 
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, int32_t *dump) {
   const uint32_t KB = mma_kb(db);
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
-  const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N;  // operand tiles + N counts
+  const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N * sizeof(int16_t);  // operand tiles + q_meta
   if (ctx->q_onehot_cap < b_bytes) {
     cudaStreamSynchronize(s);
     cudaFree(ctx->q_onehot);
@@ -577,14 +741,14 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(one-hot queries)", e);
     ctx->q_onehot_cap = b_bytes;
   }
-  uint8_t *ncount = db->mma_nsym == 4 ? ctx->q_onehot + (size_t)n_qtiles * MMA_N * KB : nullptr;
+  int16_t *meta = reinterpret_cast<int16_t *>(ctx->q_onehot + (size_t)n_qtiles * MMA_N * KB);
   MmaParams P{};
   P.sp = p;
   P.need0 = std::max(0, (int)p.L - ctx->mma_bound0);  // the initial bound is uniform over the batch
-  launch_pack_onehot(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, -P.need0, -128, ncount,
-                     ctx->q_onehot, s);
+  launch_pack_operand(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, 1, P.need0, meta,
+                      ctx->q_onehot, s);
   P.dump = dump;
-  P.q_ncount = ncount;
+  P.q_meta = meta;
   P.a_tiles = db->onehot;
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
@@ -606,11 +770,20 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint32_t n_items = P.n_qtiles * P.n_chunks;
   const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, n_items);
   cudaError_t e;
-  switch (KB) {
-    case 320: e = launch_mma<10, 5, 3>(P, grid, s); break;
-    case 160: e = launch_mma<5, 5, 3>(P, grid, s); break;
-    case 256: e = launch_mma<8, 4, 4>(P, grid, s); break;
-    default: e = launch_mma<4, 4, 4>(P, grid, s); break;  // 128
+  const bool wide = mma_pb(db->mma_nsym, db->L) == 64;
+  // Epilogue shape: 8 warps + .pack::16b TMEM loads measured best (profiles/r01_epilogue_variants.txt);
+  // SMAFA_MMA_EPI=16 / SMAFA_MMA_PACK16=0 keep the other shapes of the default encoding reachable.
+  static const int epi = getenv("SMAFA_MMA_EPI") ? atoi(getenv("SMAFA_MMA_EPI")) : 8;
+  static const bool pack16 = getenv("SMAFA_MMA_PACK16") ? atoi(getenv("SMAFA_MMA_PACK16")) != 0 : true;
+  switch (db->mma_nsym) {
+    case 5: e = wide ? launch_mma<10, 5, 3, 8, true>(P, grid, s) : launch_mma<5, 5, 3, 8, true>(P, grid, s); break;
+    case 4: e = wide ? launch_mma<8, 4, 4, 8, true>(P, grid, s) : launch_mma<4, 4, 4, 8, true>(P, grid, s); break;
+    case 2: e = wide ? launch_mma<4, 2, 4, 8, true>(P, grid, s) : launch_mma<2, 2, 4, 8, true>(P, grid, s); break;
+    default:
+      if (!wide) e = launch_mma<3, 3, 4, 8, true>(P, grid, s);
+      else if (epi == 16) e = pack16 ? launch_mma<6, 3, 4, 16, true>(P, grid, s) : launch_mma<6, 3, 4, 16, false>(P, grid, s);
+      else e = pack16 ? launch_mma<6, 3, 4, 8, true>(P, grid, s) : launch_mma<6, 3, 4, 8, false>(P, grid, s);
+      break;
   }
   if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
   return 2;

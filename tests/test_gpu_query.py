@@ -123,24 +123,47 @@ def test_distances_bit_exact(ctx, L):
 
 # ---- raw tcgen05 accumulators (pins operand layout + descriptors independently of the epilogue) ----
 
-@pytest.mark.parametrize("nsym", [4, 5])
-@pytest.mark.parametrize("L", [20, 60])
-def test_mma_accumulators_exact(L, nsym, monkeypatch):
+def _mma_accumulator_model(db_sym, q_sym, L, bound, enc):
+    """What the tcgen05 accumulators must hold for operand encoding `enc` (scan_mma.cu, "operand encodings")."""
+    need = L - bound
+    eq = db_sym[:, None, :] == q_sym[None, :, :]
+    q_base = (q_sym < 4)[None, :, :]
+    nq, nd = (q_sym == 4).sum(axis=1), (db_sym == 4).sum(axis=1)
+    if enc == 5:    # D = matches - need
+        return eq.sum(axis=2) - need
+    if enc == 4:    # D = base-base matches - max(0, need - nN_q)
+        return (eq & q_base).sum(axis=2) - np.maximum(0, need - nq)[None, :]
+    PB = 32 if L <= 30 else 64
+    alpha = 2 if enc == 2 else 1
+    w5, T = alpha + 4, enc * (PB - L) - 3
+    h = np.array([1, 1, -1, -1, 0])
+    l = np.array([1, -1, 1, -1, 0])
+    feats = [h, l] if enc == 2 else [h, l, h * l]
+    S = sum((f[db_sym][:, None, :] * f[q_sym][None, :, :]).sum(axis=2) for f in feats)
+    over = np.maximum(0, nq - (T - 1))
+    c = np.minimum(254, alpha * (L - nq) + np.maximum(0, w5 * over - 127) - 4 * need)
+    thermo = w5 * np.minimum(np.minimum(nq[None, :], nd[:, None]), T - 1) + \
+        np.minimum(127, w5 * over)[None, :] * (nd[:, None] >= T)
+    return S + c[None, :] - alpha * nd[:, None] + thermo
+
+
+@pytest.mark.parametrize("nsym", [2, 3, 4, 5])
+@pytest.mark.parametrize("L,noise", [(20, 0.05), (60, 0.05), (62, 0.6), (31, 0.1)])
+def test_mma_accumulators_exact(L, noise, nsym, monkeypatch):
     monkeypatch.setenv("SMAFA_MMA_NSYM", str(nsym))
     c = smafa_b200.Context(0, "mma")
     try:
-        db_sym = synth.make_db(1000, L=L, seed=1, noise=0.05)
-        q_sym = synth.make_queries(db_sym, 256, seed=2, noise=0.05)
+        db_sym = synth.make_db(1000, L=L, seed=1, noise=noise)
+        q_sym = synth.make_queries(db_sym, 256, seed=2, noise=noise)
         d = c.upload(synth.pack_symbols(db_sym), L)
         bound = 7
         acc = c.debug_mma_dump(d, synth.pack_symbols(q_sym), bound)
-        eq = db_sym[:128, None, :] == q_sym[None, :, :]
-        if nsym == 5:   # D = matches - need
-            want = eq.sum(axis=2) - (L - bound)
-        else:           # D = base-base matches - (need - nN_q)
-            want = (eq & (q_sym[None, :, :] < 4)).sum(axis=2) - np.maximum(0, (L - bound) - (q_sym == 4).sum(axis=1))[None, :]
+        want = _mma_accumulator_model(db_sym[:128], q_sym, L, bound, nsym)
         assert (acc == want.astype(np.int32)).all()
-        # and the 5-symbol variant still answers queries exactly
+        # the filter is conservative: every pair within the bound has a non-negative accumulator
+        dist = (db_sym[:128, None, :] != q_sym[None, :, :]).sum(axis=2)
+        assert (acc[dist <= bound] >= 0).all()
+        # and every variant still answers queries exactly
         got = c.query(d, synth.pack_symbols(q_sym), L, max_divergence=9, max_num_hits=5)
         want_rows = c_oracle.query(synth.pack_symbols(db_sym), L, synth.pack_symbols(q_sym), L, 9, 5, None)
         assert got.shape == want_rows.shape and (got == want_rows).all()
