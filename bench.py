@@ -36,6 +36,10 @@ L = 60
 Q_DEFAULT = 100_000
 D_PER_GPU = 1_000_000
 MAX_DIVERGENCE = 5
+# dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full)
+MMA_TRAFFIC_BYTES = 236.6e6 + 10.5e6
+MMA_TRAFFIC_SOURCE = ("ncu dram__bytes_read+write, profiles/r01_ncu_mma_v6pre_summary.txt (algorithmic: 192 MB "
+                      "db operand tiles + 19 MB query tiles, read once)")
 
 
 def parse_args():
@@ -159,22 +163,27 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, int8_peak):
+def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, int8_peak, mma_k):
     """Roofline of the dominant (scan) kernel.  This path is compute-bound: operands
     are reused Q x D times, compulsory HBM traffic is a few hundred MB per step."""
     secs = scan_ms / 1e3
     if kernel_used == 2:
-        ops = 2 * 5 * L  # int8 ops per comparison: one-hot(query) . one-hot(db)^T over 5 symbols x L
+        # Algorithmic work (SURVEY.md 8d): one-hot(query) . one-hot(db)^T over 5 symbols x L = 2*5*L int8 ops per
+        # comparison.  The kernel contracts over a denser operand encoding (+-1 character features of the 2-bit
+        # base code, K = mma_k per window), so it EXECUTES 2*mma_k ops per comparison: `frac` (algorithmic, the
+        # contract's definition) can exceed 1; `frac_executed` is the tensor-pipe utilisation.
+        ops = 2 * 5 * L
         achieved = pairs_per_launch * ops / secs / 1e12
+        executed = pairs_per_launch * 2 * mma_k / secs / 1e12
         # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's
         # issue-only tcgen05 kind::i8 probe (smafa_debug_mma_peak) on this GPU, same clocks.
         return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
-                "frac": achieved / int8_peak, "traffic": 399.4e6 + 5.6e6,
+                "frac": achieved / int8_peak, "traffic": MMA_TRAFFIC_BYTES,
                 "peak_source": "measured in this run: tcgen05.mma kind::i8 M128xN256xK32 issue-only probe "
                                f"on all SMs; for reference 2 x {peaks_kind} bf16_tflops = {2 * peaks['bf16_tflops']:.0f}",
-                "ops_per_comparison": ops, "executed_ops_per_comparison": 640,
-                "traffic_source": "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v3_summary.txt (algorithmic: "
-                                  "320 MB one-hot db + 32 MB query tiles)"}
+                "ops_per_comparison": ops, "executed_ops_per_comparison": 2 * mma_k,
+                "achieved_executed": executed, "frac_executed": executed / int8_peak,
+                "traffic_source": MMA_TRAFFIC_SOURCE}
     # POPC formulation: the binding unit is the POPC pipe.  Reference layout = 10 x (XOR32+POPC32)
     # per comparison (5 u64 words, src/lib.rs:85).  The bit-plane packing needs 2 (1 with early exit).
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -298,7 +307,8 @@ def main():
     if rank == 0:
         peaks, peaks_kind = load_peaks()
         st = searcher.last_stats
-        roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks, int8_peak)
+        roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks, int8_peak,
+                        searcher.db.mma_k)
         out = {
             "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,

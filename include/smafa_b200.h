@@ -173,15 +173,19 @@ uint8_t smafa_encode_symbol(uint8_t byte); /* 0 == not a nucleotide */
 int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos);
 int smafa_decode_window(const uint64_t *words, size_t len, char *out);
 
-/* ---- debug / parity hook --------------------------------------------------------------
+/* ---- debug / parity hooks -------------------------------------------------------------
  * Raw int32 accumulators of the tcgen05 formulation for the first 128 db rows x (up to) 256
- * queries: out[row*256 + col] = matches(row, col) - (L - bound).  Used by the tests to pin the
- * operand layout and descriptors of the MMA kernel independently of its epilogue. */
+ * queries.  For the 5-symbol one-hot operands out[row*256 + col] = matches(row, col) - (L - bound);
+ * the other operand encodings are documented in csrc/scan_mma.cu ("operand encodings").  Used by the
+ * tests to pin the operand layout and descriptors of the MMA kernel independently of its epilogue. */
 int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q,
                          uint32_t bound, int32_t *out /* [128][256] */);
 /* Measured dense int8 tcgen05 rate of this GPU in TOP/s (roofline denominator of the MMA kernel):
  * every SM issues mmas_per_cta back-to-back M128 x N256 x K32 kind::i8 MMAs on resident operands. */
 int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops);
+/* Contraction depth K (int8 elements per window) of the tcgen05 operands of this db, 0 if the db is
+ * not eligible for the MMA kernel: executed int8 ops per comparison = 2 * K. */
+uint32_t smafa_db_mma_k(const smafa_db *db);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ def load_library():
     l.smafa_db_file_check.argtypes = [C.c_char_p]
     l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
     l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
+    l.smafa_db_mma_k.restype = u32
+    l.smafa_db_mma_k.argtypes = [vp]
     l.smafa_encode_symbol.restype = C.c_uint8
     l.smafa_encode_symbol.argtypes = [C.c_uint8]
     l.smafa_encode_window.argtypes = [C.c_char_p, C.c_size_t, vp, C.POINTER(C.c_size_t)]
@@ -274,6 +276,11 @@ class Db:
     @property
     def size(self):
         return self._l.smafa_db_size(self._h)
+
+    @property
+    def mma_k(self):
+        """Contraction depth of the tcgen05 operands (0: db not eligible for the MMA kernel)."""
+        return int(self._l.smafa_db_mma_k(self._h))
 
     def close(self):
         if self._h:

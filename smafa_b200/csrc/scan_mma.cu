@@ -244,7 +244,8 @@ __device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
 //           N/gap rows are all-zero, so D counts base-base matches only; because N-N matches are at most
 //           the query's N count nN_q, the bias uses need_q - nN_q and the filter stays conservative:
 //           matches >= need  =>  base matches >= need - nN_q  =>  D >= 0.  Survivors are verified exactly.
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16>
+// B_BUFS = 2: the query operand of the next work item is fetched while the current item computes.
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS>
 __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
@@ -253,27 +254,27 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
   constexpr bool HAD = NSYM <= 3;            // +-1 feature encodings: bias in spare slots 0 and 1
   constexpr uint32_t A_BYTES = MMA_M * KB, B_BYTES = MMA_N * KB;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *sB = smem;
-  uint8_t *sA = smem + B_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BYTES + STAGES * A_BYTES);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  uint8_t *sB0 = smem;
+  uint8_t *sA = smem + B_BUFS * B_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BUFS * B_BYTES + STAGES * A_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
   uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(bars) + 256);  // [MMA_EPI_WARPS][MMA_LIST_CAP]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
-  static_assert(2 * STAGES + 7 <= 16, "barrier block holds 16 mbarriers");
+  static_assert(2 * STAGES + 10 <= 24, "barrier block holds 24 mbarriers");
   auto FULL = [&](uint32_t s) { return bar0 + 8 * s; };
   auto EMPTY = [&](uint32_t s) { return bar0 + 8 * (STAGES + s); };
   auto TFULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + b); };
   auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
-  const uint32_t B_FULL = bar0 + 8 * (2 * STAGES + 4), B_EMPTY = bar0 + 8 * (2 * STAGES + 5), B_READY = bar0 + 8 * (2 * STAGES + 6);
+  auto B_FULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 4 + b); };
+  auto B_EMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 6 + b); };
+  auto B_READY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 8 + b); };
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
-    mbar_init(B_FULL, 1);
-    mbar_init(B_EMPTY, 1);
-    mbar_init(B_READY, 1);
+    for (uint32_t b = 0; b < 2; ++b) { mbar_init(B_FULL(b), 1); mbar_init(B_EMPTY(b), 1); mbar_init(B_READY(b), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -292,15 +293,27 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
     // ===== producer: bulk copies + bias refresh =====
     uint32_t stage = 0, phase = 0, item_count = 0;
     int cur[8];
+    // Fetches the query operand of the work item with ordinal n (this CTA's n-th item) into buffer n % B_BUFS
+    // once the MMAs of the item that used the buffer before are done with it.
+    auto fetch_B = [&](uint32_t item, uint32_t n) {
+      if (elect_one()) {
+        const uint32_t b = n % B_BUFS, use = n / B_BUFS;
+        if (use > 0) mbar_wait(B_EMPTY(b), (use - 1) & 1);
+        mbar_expect_tx(B_FULL(b), B_BYTES);
+        bulk_g2s(smem_u32(sB0 + b * B_BYTES), P.b_tiles + (size_t)(item % P.n_qtiles) * B_BYTES, B_BYTES, B_FULL(b));
+      }
+      __syncwarp();
+    };
+    if (blockIdx.x < n_items) fetch_B(blockIdx.x, 0);
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
       const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      if (elect_one()) {
-        if (item_count > 0) mbar_wait(B_EMPTY, (item_count - 1) & 1);  // MMAs of the previous item are done with B
-        mbar_expect_tx(B_FULL, B_BYTES);
-        bulk_g2s(smem_u32(sB), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL);
-      }
-      __syncwarp();
+      const uint32_t bb_ = item_count % B_BUFS;
+      uint8_t *sB = sB0 + bb_ * B_BYTES;
+      const bool has_next = item + gridDim.x < n_items;
+      // with two buffers the next operand is requested once the ring has turned over (the item that
+      // used that buffer is then certainly finished, so the wait inside fetch_B does not stall A loads)
+      const uint32_t t_fetch = min(t_begin + (uint32_t)STAGES, t_end - 1);
       int meta[8];  // per-query constant of this lane's queries (see MmaParams::q_meta)
       // bias value of a query at bound b: one-hot = need (stored negated), +-1 features = c_q
       auto bias_of = [&](int m, int b) -> int {
@@ -346,9 +359,9 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
       };
       int4 b0 = make_int4(0, 0, 0, 0), b1 = b0;
       if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
-      mbar_wait(B_FULL, item_count & 1);
+      mbar_wait(B_FULL(bb_), (item_count / B_BUFS) & 1);
       if (dyn) apply(b0, b1);
-      if (lane == 0) mbar_arrive(B_READY);
+      if (lane == 0) mbar_arrive(B_READY(bb_));
       for (uint32_t t = t_begin; t < t_end; ++t) {
         if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
         if (elect_one()) {
@@ -357,9 +370,11 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
           bulk_g2s(smem_u32(sA + stage * A_BYTES), P.a_tiles + (size_t)t * A_BYTES, A_BYTES, FULL(stage));
         }
         __syncwarp();
+        if (B_BUFS == 2 && has_next && t == t_fetch) fetch_B(item + gridDim.x, item_count + 1);
         if (dyn) apply(b0, b1);
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
+      if (B_BUFS == 1 && has_next) fetch_B(item + gridDim.x, item_count + 1);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -370,11 +385,13 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
     // descriptors: only the 14-bit start-address field changes (stage and k-step offsets, in 16-byte units)
     const uint64_t desc_hi = ((uint64_t)(P.desc_lbo & 0x3FFFu) << 16) | ((uint64_t)(P.desc_sbo & 0x3FFFu) << 32) | (1ull << 46);
     const uint64_t adesc_base = desc_hi | (uint64_t)((smem_u32(sA) >> 4) & 0x3FFFu);
-    const uint64_t bdesc_base = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFFu);
+    const uint64_t bdesc_base0 = desc_hi | (uint64_t)((smem_u32(sB0) >> 4) & 0x3FFFu);
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
       const uint32_t chunk = item / P.n_qtiles;
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      mbar_wait(B_READY, item_count & 1);
+      const uint32_t bb_ = item_count % B_BUFS;
+      const uint64_t bdesc_base = bdesc_base0 + (uint64_t)(bb_ * (B_BYTES >> 4));
+      mbar_wait(B_READY(bb_), (item_count / B_BUFS) & 1);
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         mbar_wait(TEMPTY(buf), (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
@@ -389,7 +406,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
             tc_mma_i8<true>(d_tmem, ad + ks * 16, bdesc_base + ks * 16, idesc);  // +256 bytes per k-step
           tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
           tc_commit(TFULL(buf));    // accumulator ready for the epilogue
-          if (t + 1 == t_end) tc_commit(B_EMPTY);
+          if (t + 1 == t_end) tc_commit(B_EMPTY(bb_));
         }
         __syncwarp();
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
@@ -667,6 +684,7 @@ int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms) {
   return SMAFA_OK;
 }
 
+bool mma_supported(const smafa_db *db);
 static uint32_t mma_kb(const smafa_db *db) { return mma_pb(db->mma_nsym, db->L) * db->mma_nsym; }
 
 // The encoding a db of window length L gets when `want` is requested (+-1 features need two spare
@@ -675,6 +693,8 @@ uint32_t mma_pick_encoding(uint32_t want, uint32_t L) {
   if (want < 2 || want > 5) want = 3;
   return mma_enc_ok(want, L) ? want : 4;
 }
+
+extern "C" uint32_t smafa_db_mma_k(const smafa_db *db) { return db && mma_supported(db) ? mma_kb(db) : 0; }
 
 bool mma_supported(const smafa_db *db) { return !db->generic_only && mma_enc_ok(db->mma_nsym, db->L); }
 
@@ -717,11 +737,12 @@ void mma_db_free(smafa_db *db) {
   db->onehot_cap = 0;
 }
 
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16>
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2>
 static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
-  const size_t smem = (size_t)MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 256 +
-                      (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
-  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16>;
+  constexpr size_t smem = (size_t)B_BUFS * MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 256 +
+                          (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
+  static_assert(smem <= 232448, "more than 227 KB of shared memory");
+  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mma_threads(EPI_WARPS), smem, s>>>(P);
@@ -776,8 +797,8 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   static const int epi = getenv("SMAFA_MMA_EPI") ? atoi(getenv("SMAFA_MMA_EPI")) : 8;
   static const bool pack16 = getenv("SMAFA_MMA_PACK16") ? atoi(getenv("SMAFA_MMA_PACK16")) != 0 : true;
   switch (db->mma_nsym) {
-    case 5: e = wide ? launch_mma<10, 5, 3, 8, true>(P, grid, s) : launch_mma<5, 5, 3, 8, true>(P, grid, s); break;
-    case 4: e = wide ? launch_mma<8, 4, 4, 8, true>(P, grid, s) : launch_mma<4, 4, 4, 8, true>(P, grid, s); break;
+    case 5: e = wide ? launch_mma<10, 5, 3, 8, true, 1>(P, grid, s) : launch_mma<5, 5, 4, 8, true>(P, grid, s); break;
+    case 4: e = wide ? launch_mma<8, 4, 2, 8, true>(P, grid, s) : launch_mma<4, 4, 4, 8, true>(P, grid, s); break;
     case 2: e = wide ? launch_mma<4, 2, 4, 8, true>(P, grid, s) : launch_mma<2, 2, 4, 8, true>(P, grid, s); break;
     default:
       if (!wide) e = launch_mma<3, 3, 4, 8, true>(P, grid, s);
