@@ -92,7 +92,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -261,8 +261,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-input timing (value) ----
+    # rank 0 samples its own GPU only: one nvidia-smi poller per rank (8 of them at 50 Hz) contends for the
+    # driver lock and showed up as multi-ms launch stalls in the 8-GPU run
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     int8_peak = ctx.mma_peak_tops(50000) if rank == 0 else None
     for _ in range(a.warmup):
         rows = searcher.query_dev(q_dev, MAX_DIVERGENCE, mode_k)
@@ -282,7 +285,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall
     sampler.mark_end()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -1,6 +1,6 @@
 """Multi-GPU query: the db is row-sharded across ranks (one process per GPU), queries are
 replicated, every rank scans its shard and the per-query local candidates are merged with one
-all-gather of the padded candidate blocks (plus one of the counts) -- SURVEY.md 8e.
+all-gather of fixed-capacity candidate blocks (the row count rides in a header row) -- SURVEY.md 8e.
 
 Local candidates are a superset of the global answer: Mode A emits the local minimum and its
 ties, Mode B everything <= min(local k-th distance, --max-divergence); the local cutoff is never
@@ -24,23 +24,36 @@ def shard_bounds(D, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def exchange_candidates(local_rows, group=None):
-    """All-gathers ragged [n_r, 3] int32 candidate blocks; returns the concatenation in rank order.
-    Works on any backend (NCCL on GPUs, gloo in the CPU tests)."""
+def _pow2_at_least(n):
+    return 1 << max(0, int(n) - 1).bit_length()
+
+
+def exchange_candidates(local_rows, group=None, capacity=None):
+    """All-gathers ragged [n_r, 3] int32 candidate blocks; returns (concatenation in rank order,
+    largest per-rank count).  ONE collective on the common path: every rank contributes a block of
+    `capacity` rows behind a header row holding its true count, so no separate count exchange is
+    needed; only if some rank had more rows than `capacity` (seen by every rank in the gathered
+    headers) is the gather repeated with a capacity that fits.  Works on any backend (NCCL on GPUs,
+    gloo in the CPU tests)."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = int(local_rows.shape[0])
     if ws == 1:
-        return local_rows
+        return local_rows, n_local
     dev = local_rows.device
-    n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n_local) for _ in range(ws)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
-    pad = max(max(counts), 1)
-    block = torch.zeros((pad, 3), dtype=torch.int32, device=dev)
-    block[: local_rows.shape[0]] = local_rows
-    blocks = [torch.empty_like(block) for _ in range(ws)]
-    dist.all_gather(blocks, block, group=group)
-    return torch.cat([b[:c] for b, c in zip(blocks, counts)], dim=0)
+    cap = max(int(capacity or 0), 16)
+    while True:
+        block = torch.zeros((cap + 1, 3), dtype=torch.int32, device=dev)
+        block[0, 0] = n_local
+        keep = min(n_local, cap)
+        block[1:1 + keep] = local_rows[:keep]
+        gathered = torch.empty((ws * (cap + 1), 3), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        gathered = gathered.view(ws, cap + 1, 3)
+        counts = gathered[:, 0, 0].tolist()  # the one host read-back of the exchange
+        if max(counts) <= cap:
+            break
+        cap = _pow2_at_least(max(counts))  # identical on every rank: all of them saw the same headers
+    return torch.cat([gathered[r, 1:1 + c] for r, c in enumerate(counts)], dim=0), max(counts)
 
 
 class ShardedSearcher:
@@ -63,6 +76,7 @@ class ShardedSearcher:
         self.device = torch.device("cuda", ctx.device)
         self.hits = torch.empty((hits_capacity, 3), dtype=torch.int32, device=self.device)
         self.last_stats = None
+        self._exchange_cap = 0  # rows per rank in the candidate all-gather (adapts to the workload)
 
     def _local(self, q_dev, m, k):
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -82,7 +96,10 @@ class ShardedSearcher:
             rows = self._local(slab, max_divergence, max_num_hits)
             launches += self.last_stats["kernel_launches"]
             if self.world_size > 1:
-                union = exchange_candidates(rows, self.group).contiguous()
+                cap = self._exchange_cap or _pow2_at_least(max(4096, 2 * slab.shape[0]))
+                union, biggest = exchange_candidates(rows, self.group, cap)
+                self._exchange_cap = _pow2_at_least(max(4096, 2 * biggest))
+                union = union.contiguous()
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 n = self.ctx.merge_dev(union.data_ptr(), union.shape[0], max_divergence, max_num_hits, stream=stream)
                 launches += 8

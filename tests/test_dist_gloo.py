@@ -35,7 +35,9 @@ WORKER = textwrap.dedent("""
         if rank == 1 and m == 0:
             local = local[:0]                                        # an empty block must survive the exchange
             want_local_dropped = True
-        union = exchange_candidates(torch.from_numpy(local.astype(np.int32)))
+        # capacity 64 forces the overflow retry for the big cases, the default path for the small ones
+        union, biggest = exchange_candidates(torch.from_numpy(local.astype(np.int32)), capacity=64 if k != 10 else 1 << 16)
+        ok = ok and biggest >= local.shape[0]
         merged = np_oracle.finalize_candidates([tuple(int(x) for x in r) for r in union.numpy()], m, k)
         if m == 0:
             continue                                                 # rank 1 withheld rows on purpose
