@@ -36,6 +36,7 @@ L = 60
 Q_DEFAULT = 100_000
 D_PER_GPU = 1_000_000
 MAX_DIVERGENCE = 5
+ALPHABET = "nucleotide"
 # dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full)
 MMA_TRAFFIC_BYTES = 236.6e6 + 10.5e6
 MMA_TRAFFIC_SOURCE = ("ncu dram__bytes_read+write, profiles/r01_ncu_mma_v6pre_summary.txt (algorithmic: 192 MB "
@@ -55,15 +56,23 @@ def parse_args():
     ap.add_argument("--db-per-gpu", type=int, default=D_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--max-divergence", default=str(MAX_DIVERGENCE), help="integer or 'none' (default 5 = configs[1])")
+    ap.add_argument("--max-divergence", default=None, help="integer or 'none' (default 5 = configs[1]; protein: none)")
+    ap.add_argument("--alphabet", default="nucleotide", choices=["nucleotide", "protein"],
+                    help="protein = the configs[3] shape (20-aa windows, --max-num-hits 10), an extension without reference parity")
     a = ap.parse_args()
+    global L
+    if a.alphabet == "protein":
+        L, a.mode = 20, "b"
+        a.max_divergence = a.max_divergence or "none"
+    a.max_divergence = a.max_divergence or str(MAX_DIVERGENCE)
     MAX_DIVERGENCE = None if a.max_divergence.lower() == "none" else int(a.max_divergence)
     return a
 
 
 def workload_name(a, n):
     k = "" if a.mode == "a" else " --max-num-hits 10"
-    return (f"synthetic {L}-nt SingleM windows: {a.queries} queries x {a.db_per_gpu * n} db "
+    unit = "nt" if a.alphabet == "nucleotide" else "aa protein"
+    return (f"synthetic {L}-{unit} SingleM windows: {a.queries} queries x {a.db_per_gpu * n} db "
             f"({a.db_per_gpu}/GPU row shard), " + (f"--max-divergence {MAX_DIVERGENCE}" if MAX_DIVERGENCE is not None else "no max-divergence") + k)
 
 
@@ -71,6 +80,11 @@ def make_inputs(a, rank, n):
     from smafa_b200 import synth
     # every rank derives its own shard from a rank-specific seed; queries come from shard 0's
     # generator state so they are identical on every rank
+    if a.alphabet == "protein":
+        db0 = synth.make_db_aa(a.db_per_gpu, L=L, seed=synth.SEED_PROTEIN)
+        q_sym = synth.make_queries_aa(db0, a.queries, seed=synth.SEED_PROTEIN + 1)
+        shard = db0 if rank == 0 else synth.make_db_aa(a.db_per_gpu, L=L, seed=synth.SEED_PROTEIN + 7919 * rank)
+        return synth.pack_symbols_aa(shard), synth.pack_symbols_aa(q_sym)
     db0 = synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB)
     q_sym = synth.make_queries(db0, a.queries, seed=synth.SEED_QUERY)
     shard = db0 if rank == 0 else synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB + 7919 * rank)
@@ -137,6 +151,7 @@ def cpu_baseline(db, q, seconds, mode_k):
     """Times the oracle's query (all host threads) on a bounded prefix of the same queries."""
     from oracle import c_oracle
     c_oracle.build()
+    c_oracle.set_alphabet(1 if ALPHABET == "protein" else 0)
     threads = os.cpu_count() or 1
     D = db.shape[0]
     probe = min(q.shape[0], 4 * threads)
@@ -172,7 +187,7 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
         # comparison.  The kernel contracts over a denser operand encoding (+-1 character features of the 2-bit
         # base code, K = mma_k per window), so it EXECUTES 2*mma_k ops per comparison: `frac` (algorithmic, the
         # contract's definition) can exceed 1; `frac_executed` is the tensor-pipe utilisation.
-        ops = 2 * 5 * L
+        ops = 2 * (5 if ALPHABET == "nucleotide" else 23) * L  # one-hot symbols x positions
         achieved = pairs_per_launch * ops / secs / 1e12
         executed = pairs_per_launch * 2 * mma_k / secs / 1e12
         # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's
@@ -226,7 +241,9 @@ def run_reference(a):
 
 
 def main():
+    global ALPHABET
     a = parse_args()
+    ALPHABET = a.alphabet
     if a.impl == "reference":
         return run_reference(a)
 
@@ -248,6 +265,7 @@ def main():
 
     db, q = make_inputs(a, rank, world)
     ctx = smafa_b200.Context(local_rank, a.kernel)
+    ctx.set_alphabet(a.alphabet)
     searcher = ShardedSearcher(ctx, db, L, world_size=world, rank=rank, presharded=True)
     mode_k = None if a.mode == "a" else 10
     q_pinned = torch.from_numpy(q.view(np.int64)).pin_memory()

@@ -57,6 +57,17 @@ typedef enum smafa_kernel {
   SMAFA_KERNEL_MMA = 2   /* tcgen05 int8 MMA over one-hot operands, TMEM-drain epilogue */
 } smafa_kernel;
 
+/* Alphabets.  NUCLEOTIDE is the reference (src/lib.rs:167-184).  PROTEIN is an EXTENSION of this
+ * build -- the reference panics on amino-acid bytes (src/lib.rs:35-42), so there is no reference
+ * parity for it: same word geometry (12 five-bit groups per u64), but every group holds
+ * a symbol NUMBER (1..20 = ACDEFGHIKLMNPQRSTVWY, 21 = X/B/Z/J/U/O, 22 = '-', 23 = '*') instead of a
+ * one-hot code, and the distance is the number of positions whose symbols differ (X-X, gap-gap match,
+ * mirroring the reference's N rule). */
+typedef enum smafa_alphabet {
+  SMAFA_ALPHABET_NUCLEOTIDE = 0,
+  SMAFA_ALPHABET_PROTEIN = 1
+} smafa_alphabet;
+
 typedef struct smafa_ctx smafa_ctx;
 typedef struct smafa_db smafa_db;
 
@@ -88,6 +99,9 @@ void smafa_ctx_destroy(smafa_ctx *ctx);
  * ctx == NULL).  Never NULL. */
 const char *smafa_last_error(const smafa_ctx *ctx);
 int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel);
+/* Alphabet of the dbs uploaded from now on (a db keeps the alphabet it was uploaded with; queries are
+ * read in their db's alphabet), of smafa_cluster input and of the *_file calls on this context. */
+int smafa_ctx_set_alphabet(smafa_ctx *ctx, int alphabet /* smafa_alphabet */);
 /* Candidate-buffer capacity in rows (testing hook for the overflow/retry path; 0 = default). */
 int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows);
 
@@ -160,6 +174,7 @@ void smafa_free(void *p);
  * says whether the reference would have exited 1 (SMAFA_E_IO) or panicked (any other code);
  * smafa_last_error(NULL) holds the message. */
 int smafa_makedb_file(const char *subject_fasta, const char *db_path);
+int smafa_makedb_file_alphabet(const char *subject_fasta, const char *db_path, int alphabet);
 int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fasta,
                      int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
                      int out_fd);
@@ -172,6 +187,9 @@ int smafa_db_file_check(const char *db_path);
 uint8_t smafa_encode_symbol(uint8_t byte); /* 0 == not a nucleotide */
 int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos);
 int smafa_decode_window(const uint64_t *words, size_t len, char *out);
+uint8_t smafa_encode_symbol_alphabet(uint8_t byte, int alphabet);
+int smafa_encode_window_alphabet(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos, int alphabet);
+int smafa_decode_window_alphabet(const uint64_t *words, size_t len, char *out, int alphabet);
 
 /* ---- debug / parity hooks -------------------------------------------------------------
  * Raw int32 accumulators of the tcgen05 formulation for the first 128 db rows x (up to) 256

@@ -43,6 +43,11 @@ def lib():
     return _lib
 
 
+def set_alphabet(alphabet):
+    """0 = nucleotide (reference), 1 = protein (extension, parity unpinned).  Process-wide."""
+    lib().orc_set_alphabet(int(alphabet))
+
+
 def _opt(v):
     return -1 if v is None else int(v)
 

@@ -64,11 +64,15 @@ def decode(words, L):
     return "".join(_DEC[(int(words[i // 12]) >> (5 * (i % 12))) & 31] for i in range(L))
 
 
-def distances(db, q):
-    """src/lib.rs:80-88: db [D, W], q [W] -> int64 [D]"""
+def distances(db, q, alphabet=0):
+    """src/lib.rs:80-88: db [D, W], q [W] -> int64 [D].  alphabet=1: the protein extension (parity
+    unpinned -- the reference has no amino-acid mode): positions whose 5-bit symbols differ."""
     if db.shape[0] == 0:
         return np.zeros(0, dtype=np.int64)
     x = np.bitwise_xor(db, q[None, :])
+    if alphabet:
+        x = x | (x >> np.uint64(1)) | (x >> np.uint64(2)) | (x >> np.uint64(3)) | (x >> np.uint64(4))
+        return np.bitwise_count(x & np.uint64(0x0084210842108421)).sum(axis=1).astype(np.int64)
     return np.bitwise_count(x).sum(axis=1).astype(np.int64) // 2
 
 

@@ -29,8 +29,31 @@ void orc_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------ symbol rules */
 
+/* Alphabet switch.  0 = nucleotide = the reference.  1 = protein: an EXTENSION of the B200 build
+ * (the reference panics on amino-acid bytes, src/lib.rs:35-42), PARITY UNPINNED -- there is no
+ * reference behaviour to pin it to.  Definition: symbol numbers 1..20 = ACDEFGHIKLMNPQRSTVWY,
+ * 21 = X/B/Z/J/U/O, 22 = '-', 23 = '*' in the same 5-bit groups; distance = number of positions whose
+ * symbols differ.  Process-wide (set before any threads are started). */
+static int g_alphabet = 0;
+void orc_set_alphabet(int alphabet) { g_alphabet = alphabet; }
+int orc_get_alphabet(void) { return g_alphabet; }
+
+static uint8_t aa_encode_single(uint8_t b) {
+  static const char aa[] = "ACDEFGHIKLMNPQRSTVWY";
+  if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);
+  for (int i = 0; aa[i]; ++i)
+    if (b == (uint8_t)aa[i]) return (uint8_t)(i + 1);
+  switch (b) {
+    case 'X': case 'B': case 'Z': case 'J': case 'U': case 'O': return 21;
+    case '-': return 22;
+    case '*': return 23;
+    default: return 0;
+  }
+}
+
 /* src/lib.rs:167-184 (create_lut) + src/lib.rs:190-196 (encode_single) */
 uint8_t orc_encode_single(uint8_t b) {
+  if (g_alphabet) return aa_encode_single(b);
   switch (b) {
     case 'A': case 'a': return 0x10;
     case 'C': case 'c': return 0x08;
@@ -54,8 +77,8 @@ int orc_encode(const char *id, const uint8_t *seq, size_t len, uint64_t *out) {
     uint8_t c = orc_encode_single(seq[p]);
     if (!c)
       return fail(ORC_PANIC,
-                  "Byte %u cannot be interpreted as nucleotide, in sequence \"%s\" at position %zu",
-                  (unsigned)seq[p], id ? id : "", p);
+                  "Byte %u cannot be interpreted as %s, in sequence \"%s\" at position %zu",
+                  (unsigned)seq[p], g_alphabet ? "amino acid" : "nucleotide", id ? id : "", p);
     out[p / 12] |= (uint64_t)c << (5 * (p % 12));
   }
   return ORC_OK;
@@ -65,6 +88,12 @@ int orc_encode(const char *id, const uint8_t *seq, size_t len, uint64_t *out) {
 int orc_decode(const uint64_t *words, size_t len, char *out) {
   for (size_t i = 0; i < len; ++i) {
     unsigned b = (unsigned)((words[i / 12] >> (5 * (i % 12))) & 31u);
+    if (g_alphabet) {
+      static const char aa[] = "?ACDEFGHIKLMNPQRSTVWYX-*";
+      if (b < 1 || b > 23) return fail(ORC_PANIC, "Invalid character in query sequence: %u", b);
+      out[i] = aa[b];
+      continue;
+    }
     switch (b) {
       case 0x10: out[i] = 'A'; break;
       case 0x08: out[i] = 'C'; break;
@@ -82,6 +111,12 @@ void orc_distances(const uint64_t *db, size_t n, size_t W, const uint64_t *q, si
   for (size_t i = 0; i < n; ++i) {
     const uint64_t *w = db + i * W;
     size_t s = 0;
+    if (g_alphabet) { /* protein extension: positions whose 5-bit symbols differ */
+      for (size_t j = 0; j < W; ++j)
+        for (int g = 0; g < 12; ++g) s += (((w[j] ^ q[j]) >> (5 * g)) & 31u) != 0;
+      dist[i] = s;
+      continue;
+    }
     for (size_t j = 0; j < W; ++j) s += (size_t)__builtin_popcountll(w[j] ^ q[j]);
     dist[i] = s / 2;
   }

@@ -57,6 +57,11 @@ typedef struct {
 
 const char *orc_last_error(void);
 
+/* 0 = nucleotide (the reference, default); 1 = protein, the B200 build's extension -- PARITY UNPINNED
+ * (the reference cannot process amino acids at all; see smafa_oracle.c "symbol rules"). */
+void orc_set_alphabet(int alphabet);
+int orc_get_alphabet(void);
+
 /* src/lib.rs:167-196: byte -> 5-bit one-hot code, 0 = invalid. */
 uint8_t orc_encode_single(uint8_t byte);
 size_t orc_words_for_len(size_t len); /* ceil(len/12), src/lib.rs:32 */

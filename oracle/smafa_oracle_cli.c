@@ -42,6 +42,7 @@ int main(int argc, char **argv) {
   for (; i < argc; ++i) {
     const char *a = argv[i];
     if (is_flag(a, "-v", "--verbose") || is_flag(a, NULL, "--quiet")) continue;
+    if (is_flag(a, NULL, "--protein")) { orc_set_alphabet(1); continue; } /* extension, parity unpinned */
     if (!is_query && is_flag(a, "-q", NULL)) continue;
     if (is_flag(a, "-i", "--input")) {
       if (strcmp(cmd, "count") == 0) {

@@ -69,6 +69,7 @@ def load_library():
     l.smafa_ctx_destroy.restype = None
     l.smafa_ctx_set_kernel.argtypes = [vp, C.c_int]
     l.smafa_ctx_set_candidate_capacity.argtypes = [vp, u64]
+    l.smafa_ctx_set_alphabet.argtypes = [vp, C.c_int]
     l.smafa_db_upload.argtypes = [vp, vp, u64, u32, u64, C.POINTER(vp)]
     l.smafa_db_append.argtypes = [vp, vp, vp, u64]
     l.smafa_db_size.restype = u64
@@ -88,6 +89,7 @@ def load_library():
     l.smafa_free.argtypes = [vp]
     l.smafa_free.restype = None
     l.smafa_makedb_file.argtypes = [C.c_char_p, C.c_char_p]
+    l.smafa_makedb_file_alphabet.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     l.smafa_query_file.argtypes = [vp, C.c_char_p, C.c_char_p, i64, i64, i64, C.c_int]
     l.smafa_cluster_file.argtypes = [vp, C.c_char_p, u32, C.c_int]
     l.smafa_count_files.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, C.c_int]
@@ -100,6 +102,10 @@ def load_library():
     l.smafa_encode_symbol.argtypes = [C.c_uint8]
     l.smafa_encode_window.argtypes = [C.c_char_p, C.c_size_t, vp, C.POINTER(C.c_size_t)]
     l.smafa_decode_window.argtypes = [vp, C.c_size_t, C.c_char_p]
+    l.smafa_encode_symbol_alphabet.restype = C.c_uint8
+    l.smafa_encode_symbol_alphabet.argtypes = [C.c_uint8, C.c_int]
+    l.smafa_encode_window_alphabet.argtypes = [C.c_char_p, C.c_size_t, vp, C.POINTER(C.c_size_t), C.c_int]
+    l.smafa_decode_window_alphabet.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_int]
     _lib = l
     return l
 
@@ -139,6 +145,14 @@ class Context:
 
     def set_kernel(self, kernel):
         rc = self._l.smafa_ctx_set_kernel(self._h, _KERNELS[kernel] if isinstance(kernel, str) else kernel)
+        if rc:
+            _raise(rc, self._h)
+
+    def set_alphabet(self, alphabet):
+        """'nucleotide' (the reference) or 'protein' (extension; see include/smafa_b200.h): applies to the dbs
+        uploaded afterwards, to cluster() input and to the file-level calls on this context."""
+        a = {"nucleotide": 0, "protein": 1}[alphabet] if isinstance(alphabet, str) else int(alphabet)
+        rc = self._l.smafa_ctx_set_alphabet(self._h, a)
         if rc:
             _raise(rc, self._h)
 
@@ -296,9 +310,9 @@ class Db:
 
 # ---- file-level mirror of the reference's public functions ---------------------------------
 
-def makedb(subject_fasta, db_path):
-    """smafa::makedb (reference src/lib.rs:137-165).  Host only."""
-    rc = load_library().smafa_makedb_file(os.fsencode(subject_fasta), os.fsencode(db_path))
+def makedb(subject_fasta, db_path, protein=False):
+    """smafa::makedb (reference src/lib.rs:137-165).  Host only.  protein=True: the amino-acid extension."""
+    rc = load_library().smafa_makedb_file_alphabet(os.fsencode(subject_fasta), os.fsencode(db_path), 1 if protein else 0)
     if rc:
         _raise(rc)
 

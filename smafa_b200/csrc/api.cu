@@ -124,6 +124,13 @@ extern "C" int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel) {
   return SMAFA_OK;
 }
 
+extern "C" int smafa_ctx_set_alphabet(smafa_ctx *ctx, int alphabet) {
+  if (!ctx || (alphabet != SMAFA_ALPHABET_NUCLEOTIDE && alphabet != SMAFA_ALPHABET_PROTEIN))
+    return fail(ctx, SMAFA_E_INVALID, "bad alphabet selector %d", alphabet);
+  ctx->alphabet = alphabet;
+  return SMAFA_OK;
+}
+
 extern "C" int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows) {
   if (!ctx) return SMAFA_E_INVALID;
   cudaSetDevice(ctx->device);
@@ -205,7 +212,7 @@ static int db_add_rows(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64
   if (rc) return rc;
   CU(cudaMemcpyAsync(db->ref + db->D * db->W, enc, n * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   if (db->row_words)
-    launch_pack_planes(db->ref + db->D * db->W, (uint32_t)n, db->W, db->L, db->row_words,
+    launch_pack_planes(db->ref + db->D * db->W, (uint32_t)n, db->W, db->L, db->row_words, db->alphabet,
                        db->planes + db->D * db->row_words, db->invalid_flag, ctx->stream);
   rc = mma_db_pack(ctx, db, db->D, n);
   if (rc) return rc;
@@ -232,7 +239,8 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
   db->row_words = row_words_for(L);
   db->generic_only = (db->row_words == 0);
   db->subject_offset = subject_offset;
-  db->mma_nsym = mma_pick_encoding(ctx->mma_nsym, L);
+  db->alphabet = ctx->alphabet;
+  db->mma_nsym = mma_pick_encoding(ctx->mma_nsym, L, db->alphabet);
   cudaError_t e = cudaMalloc((void **)&db->invalid_flag, sizeof(int));
   if (e != cudaSuccess) { delete db; return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(db->invalid_flag, 0, sizeof(int), ctx->stream);
@@ -283,7 +291,7 @@ extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_
   for (uint64_t q0 = 0; q0 < Q && rc == SMAFA_OK; q0 += qb) {
     uint64_t nq = std::min(qb, Q - q0);
     cudaMemcpyAsync(dq, q_enc + q0 * db->W, nq * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    launch_distances(dq, (uint32_t)nq, db->ref, (uint32_t)D, db->W, dout, ctx->stream);
+    launch_distances(dq, (uint32_t)nq, db->ref, (uint32_t)D, db->W, db->alphabet, dout, ctx->stream);
     cudaMemcpyAsync(out + q0 * D, dout, nq * D * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "smafa_distances: %s", cudaGetErrorString(e2));
@@ -372,6 +380,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   p.d_end = (uint32_t)db->D;
   p.W = db->W;
   p.L = db->L;
+  p.alphabet = db->alphabet;
   p.mode = plan.mode;
   p.k = plan.k_scan;
   p.bound = ctx->bound;
@@ -400,7 +409,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       launches += launch_scan_generic(p, chunk, s);
     } else {
       if ((rc = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)Qb + 256) * db->row_words))) return rc;
-      launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, ctx->q_planes, q_invalid, s);
+      launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
       launches += 1;
       p.q_planes = ctx->q_planes;
       // No useful starting bound (no or a loose --max-divergence): estimate one on a strided db

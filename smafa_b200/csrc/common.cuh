@@ -18,6 +18,27 @@ namespace smafa {
 
 enum ScanMode : int { MODE_FIXED = 0, MODE_MIN = 1, MODE_KTH = 2 };
 
+// Alphabets.  NUC is the reference's encoding (5-bit ONE-HOT codes, src/lib.rs:167-184).  AA is this
+// build's protein extension (the reference panics on amino-acid bytes, src/lib.rs:35-42):
+// same word geometry -- 12 five-bit groups per u64 -- but each group holds a symbol NUMBER 1..23
+// (20 amino acids, X, '-', '*'), and the distance is the number of positions whose groups differ.
+enum Alphabet : int { ALPHA_NUC = 0, ALPHA_AA = 1 };
+
+// Filter class of a protein symbol, expressed as a nucleotide one-hot code (16, 8, 4, 2; 1 = the N-like
+// class of X, '-' and '*'; 0 = not a symbol).  Both scan kernels filter protein windows on this 4-class
+// image with their nucleotide machinery -- equal symbols are in equal classes, so class matches >= true
+// matches and the filter stays conservative -- and re-evaluate survivors exactly on the symbol words.
+// The classes split the usual substitution pairs (I/L/V, D/E, K/R, S/T, N/Q, F/Y) and are roughly balanced
+// by background frequency.
+__host__ __device__ __forceinline__ uint32_t aa_class_code(uint32_t sym) {
+  //                         -   A  C  D  E  F  G  H  I  K   L   M  N   P  Q  R  S   T  V  W  Y  X  -  *
+  constexpr uint8_t T[32] = {0, 8, 16, 2, 8, 8, 4, 8, 4, 16, 16, 4, 16, 2, 4, 4, 16, 8, 2, 4, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0};
+  return T[sym & 31u];
+}
+__host__ __device__ __forceinline__ uint32_t filter_code(uint32_t code, int alphabet) {
+  return alphabet == ALPHA_NUC ? code : aa_class_code(code);
+}
+
 // Candidate rows are stored as one sortable 64-bit key:
 //   bits 63..44 query (batch-local, < 2^20) | bits 43..32 distance (< 2^12) | bits 31..0 subject
 constexpr int KEY_Q_SHIFT = 44;
@@ -44,6 +65,7 @@ struct ScanParams {
   uint32_t D;
   uint32_t d_begin, d_end;   // window range covered by this launch
   uint32_t W, L;
+  int alphabet;              // Alphabet of q_ref / d_ref (planes and MMA operands hold the filter classes)
   // running state
   int mode;
   uint32_t k;                // MODE_KTH
@@ -116,11 +138,20 @@ __device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, i
   }
 }
 
-// Exact reference distance on the reference word layout (src/lib.rs:80-88).
-__device__ __forceinline__ int ref_distance(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint32_t W) {
+// Exact distance on the reference word layout.  NUC: popcount(a^b)/2 (src/lib.rs:80-88).  AA: number of
+// 5-bit groups in which the two words differ.
+__device__ __forceinline__ int ref_distance(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint32_t W,
+                                            int alphabet) {
   int s = 0;
-  for (uint32_t w = 0; w < W; ++w) s += __popcll(a[w] ^ b[w]);
-  return s >> 1;
+  if (alphabet == ALPHA_NUC) {
+    for (uint32_t w = 0; w < W; ++w) s += __popcll(a[w] ^ b[w]);
+    return s >> 1;
+  }
+  for (uint32_t w = 0; w < W; ++w) {
+    const uint64_t x = a[w] ^ b[w];
+    s += __popcll((x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4)) & 0x0084210842108421ull);  // bit 0 of each group
+  }
+  return s;
 }
 
 }  // namespace smafa

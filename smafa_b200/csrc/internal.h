@@ -17,6 +17,7 @@ struct smafa_ctx {
   // rate does not depend on how tight the bound is.  Tiny query batches stay on the POPC kernel.
   bool auto_prefers_mma = true;
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
+  int alphabet = 0;               // Alphabet of the dbs uploaded next and of smafa_cluster input (smafa_ctx_set_alphabet)
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
   int32_t *mma_dump = nullptr;    // debug hook (smafa_debug_mma_dump)
   int mma_bound0 = 0;             // initial bound of the batch being scanned (bias of the query operand)
@@ -46,6 +47,7 @@ struct smafa_db {
   uint64_t D = 0, cap = 0;
   uint32_t L = 0, W = 0, row_words = 0;
   uint64_t subject_offset = 0;
+  int alphabet = 0;           // smafa::Alphabet of `ref` (and of every query batch run against this db)
   bool generic_only = false;  // invalid codes or L > 64: reference-layout kernel only
   uint64_t *ref = nullptr;    // [cap][W]
   uint32_t *planes = nullptr; // [cap + pad][row_words]
@@ -61,7 +63,7 @@ void smafa_set_global_error(const std::string &s);
 
 // scan_mma.cu
 bool mma_supported(const smafa_db *db);
-uint32_t mma_pick_encoding(uint32_t want, uint32_t L);
+uint32_t mma_pick_encoding(uint32_t want, uint32_t L, int alphabet);
 int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows);
 int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n);
 void mma_db_free(smafa_db *db);

@@ -10,7 +10,7 @@ namespace smafa {
 struct ScanParams;
 
 // pack.cu
-void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words,
+void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words, int alphabet,
                         uint32_t *planes, int *invalid, cudaStream_t s);
 void launch_init_bound(int *bound, uint32_t Q, int v, cudaStream_t s);
 
@@ -19,7 +19,7 @@ int launch_scan_popc(const ScanParams &p, bool early, uint32_t chunk, cudaStream
 int launch_scan_generic(const ScanParams &p, uint32_t chunk, cudaStream_t s);
 // Bound estimator on every tile_stride-th 256-window tile (no emission); see scan_popc.cu
 int launch_bound_prepass(const ScanParams &p, uint32_t tile_stride, cudaStream_t s);
-void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W,
+void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W, int alphabet,
                       uint16_t *out, cudaStream_t s);
 int popc_tile_rows();
 

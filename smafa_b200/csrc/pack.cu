@@ -10,6 +10,7 @@
 //              mismatch).  Row = [H0 Lo0 H1 Lo1 | N0 N1 0 0] (32 B, L<=64) or
 //              [H0 Lo0 N0 0] (16 B, L<=32): one or two aligned 16-byte loads per window.
 //          (2) one-hot int8 rows for the tcgen05 kernel (see scan_mma.cu for the tile layout).
+// Protein windows (ALPHA_AA, common.cuh) are packed through their 4-class filter image.
 // Windows holding anything but the five valid codes (possible only in a hand-made db file) set
 // the `invalid` flag; the caller then uses the generic reference-layout kernel, which computes
 // popcount(a^b)/2 like the reference for arbitrary words.
@@ -19,14 +20,15 @@
 namespace smafa {
 
 __global__ void pack_planes_kernel(const uint64_t *__restrict__ ref, uint32_t n, uint32_t W, uint32_t L,
-                                   uint32_t row_words, uint32_t *__restrict__ planes, int *__restrict__ invalid) {
+                                   uint32_t row_words, int alphabet, uint32_t *__restrict__ planes,
+                                   int *__restrict__ invalid) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t *w = ref + (size_t)i * W;
   uint32_t h[2] = {0, 0}, lo[2] = {0, 0}, nn[2] = {0, 0};
   bool bad = false;
   for (uint32_t p = 0; p < L; ++p) {
-    uint32_t code = (uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u;
+    uint32_t code = filter_code((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u, alphabet);
     uint32_t bit = 1u << (p & 31), s = p >> 5;
     switch (code) {
       case 16: break;
@@ -53,10 +55,10 @@ __global__ void pack_planes_kernel(const uint64_t *__restrict__ ref, uint32_t n,
   }
 }
 
-void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words,
+void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words, int alphabet,
                         uint32_t *planes, int *invalid, cudaStream_t s) {
   if (n == 0) return;
-  pack_planes_kernel<<<(n + 255) / 256, 256, 0, s>>>(ref, n, W, L, row_words, planes, invalid);
+  pack_planes_kernel<<<(n + 255) / 256, 256, 0, s>>>(ref, n, W, L, row_words, alphabet, planes, invalid);
 }
 
 __global__ void init_bound_kernel(int *bound, uint32_t Q, int v) {

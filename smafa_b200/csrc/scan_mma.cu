@@ -65,9 +65,18 @@ struct MmaParams {
 //   spare 2   : db -alpha*nN_d,  query 1
 //   spare 3+t : thermometer code of the N counts, t < T: db [nN_d >= t+1], query (alpha+4)*[nN_q >= t+1];
 //               the last level carries (alpha+4)*max(0, nN_q-(T-1)) so the sum is >= min(nN_q, nN_d) >= nNN.
+// ENC = 20: protein windows of L <= 20 (ALPHA_AA): one-hot over the 20 amino acids, K index = symbol*20 + position
+//           (400) + 16 spare slots = 416 (13 k-steps).  X / '-' / '*' rows are all-zero like N in ENC 4:
+//           D = amino-acid matches - (need - nX_q).  Protein windows longer than 20 (and the POPC kernel) filter
+//           on the 4-class image of the symbols instead (common.cuh aa_class_code) with ENC 2..5.
 // Every variant is a conservative filter; survivors are re-evaluated exactly before they are emitted.
-__host__ __device__ __forceinline__ uint32_t mma_pb(uint32_t enc, uint32_t L) { return L <= (enc <= 3 ? 30u : 31u) ? 32u : 64u; }
-__host__ __device__ __forceinline__ bool mma_enc_ok(uint32_t enc, uint32_t L) { return L >= 1 && L <= (enc <= 3 ? 62u : 63u); }
+constexpr uint32_t MMA_ENC_AA = 20, MMA_AA_POS = 20, MMA_AA_KB = 416;
+__host__ __device__ __forceinline__ uint32_t mma_pb(uint32_t enc, uint32_t L) {
+  return enc == MMA_ENC_AA ? MMA_AA_POS : (L <= (enc <= 3 ? 30u : 31u) ? 32u : 64u);
+}
+__host__ __device__ __forceinline__ bool mma_enc_ok(uint32_t enc, uint32_t L) {
+  return L >= 1 && L <= (enc == MMA_ENC_AA ? MMA_AA_POS : (enc <= 3 ? 62u : 63u));
+}
 // k index of spare slot si (feature-block major)
 __host__ __device__ __forceinline__ uint32_t had_spare_k(uint32_t si, uint32_t PB, uint32_t L) {
   const uint32_t gap = PB - L;
@@ -189,7 +198,7 @@ constexpr int MMA_LIST_CAP = 256;  // survivors per epilogue warp between drains
 
 __device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uint32_t j, int &d, int &bnd) {
   if (q >= sp.Q || j >= sp.d_end) return false;
-  d = ref_distance(sp.q_ref + (size_t)q * sp.W, sp.d_ref + (size_t)j * sp.W, sp.W);
+  d = ref_distance(sp.q_ref + (size_t)q * sp.W, sp.d_ref + (size_t)j * sp.W, sp.W, sp.alphabet);
   bnd = __ldcg(sp.bound + q);
   return d <= bnd;
 }
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
   constexpr uint32_t PB = KB / NSYM;         // positions per symbol / feature block
-  constexpr uint32_t BIAS_K = PB - 1;        // one-hot encodings: symbol A, position PB-1
+  constexpr uint32_t BIAS_K = NSYM == (int)MMA_ENC_AA ? MMA_ENC_AA * MMA_AA_POS : PB - 1;  // one-hot: symbol A, position PB-1
   constexpr bool HAD = NSYM <= 3;            // +-1 feature encodings: bias in spare slots 0 and 1
   constexpr uint32_t A_BYTES = MMA_M * KB, B_BYTES = MMA_N * KB;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         if constexpr (HAD) return min(254, m - 4 * need);
         else return max(0, min(need - m, 127));
       };
-      const uint32_t k0 = had_spare_k(0, PB, sp.L), k1 = had_spare_k(1, PB, sp.L);
+      const uint32_t k0 = HAD ? had_spare_k(0, PB, sp.L) : 0, k1 = HAD ? had_spare_k(1, PB, sp.L) : 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t q = qt * MMA_N + lane * 8 + i;
@@ -562,16 +571,40 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
 // their per-query constant in meta[].
 __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
                                     uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query,
-                                    int need0, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
-  const uint32_t chunks = KB / 16, PB = KB / enc, gap = PB - L;
+                                    int need0, int alphabet, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
+  const bool aa_exact = enc == MMA_ENC_AA;
+  const uint32_t chunks = KB / 16, PB = aa_exact ? MMA_AA_POS : KB / enc, gap = PB - L;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t row = row_begin + (uint32_t)(idx / chunks), c = (uint32_t)(idx % chunks);
   if (row >= row_end) return;
   const bool valid = row < n_valid, had = enc <= 3;
   const uint64_t *w = ref + (size_t)row * W;
-  int nN = 0;  // N/gap positions: code 1 = bit 0 of a 5-bit group
-  if (valid)
-    for (uint32_t i = 0; i < W; ++i) nN += __popcll(w[i] & 0x0084210842108421ull);
+  int nN = 0;  // N/gap positions: code 1 = bit 0 of a 5-bit group (protein: symbols of the N-like filter class)
+  if (valid) {
+    if (alphabet == ALPHA_NUC)
+      for (uint32_t i = 0; i < W; ++i) nN += __popcll(w[i] & 0x0084210842108421ull);
+    else
+      for (uint32_t x = 0; x < L; ++x) nN += aa_class_code((uint32_t)(w[x / 12] >> (5 * (x % 12))) & 31u) == 1u;
+  }
+  if (aa_exact) {  // one-hot over the symbol numbers 1..20; bias in slot 400
+    uint32_t oo[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (uint32_t i = 0; i < 16; ++i) {
+      const uint32_t k = c * 16 + i, sy = k / MMA_AA_POS, p = k % MMA_AA_POS;
+      int v = 0;
+      if (k < MMA_ENC_AA * MMA_AA_POS) {
+        if (valid && p < L) v = ((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u) == sy + 1;
+      } else if (k == MMA_ENC_AA * MMA_AA_POS) {
+        v = !is_query ? 1 : (valid ? -max(0, min(need0 - nN, 127)) : -128);
+      }
+      oo[i >> 2] |= ((uint32_t)v & 0xffu) << (8 * (i & 3));
+    }
+    if (is_query && meta != nullptr && c == 0) meta[row] = (int16_t)(valid ? nN : 0);
+    const uint32_t tile = row / rows_per_tile, r = row % rows_per_tile;
+    *reinterpret_cast<uint4 *>(out + (size_t)tile * rows_per_tile * KB + tile_offset(r, c * 16, KB)) =
+        make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    return;
+  }
   const int alpha = enc == 2 ? 2 : 1, w5 = alpha + 4, T = (int)(enc * gap) - 3;
   const int over = max(0, nN - (T - 1));
   int qbase = 0, cq = 0;
@@ -586,7 +619,7 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
     int v = 0;
     if (p < L) {
       if (valid) {
-        const uint32_t code = (uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u;
+        const uint32_t code = filter_code((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u, alphabet);
         if (!had) {
           v = code == (16u >> f);  // A C G T N
         } else if (code >= 2 && (code & (code - 1)) == 0) {
@@ -621,11 +654,11 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
 
 static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
                                 uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query, int need0,
-                                int16_t *meta, uint8_t *out, cudaStream_t s) {
+                                int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)(row_end - row_begin) * (KB / 16);
   pack_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
-                                                                enc, is_query, need0, meta, out);
+                                                                enc, is_query, need0, alphabet, meta, out);
 }
 
 // Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten
@@ -685,11 +718,16 @@ int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms) {
 }
 
 bool mma_supported(const smafa_db *db);
-static uint32_t mma_kb(const smafa_db *db) { return mma_pb(db->mma_nsym, db->L) * db->mma_nsym; }
+static uint32_t mma_kb(const smafa_db *db) {
+  return db->mma_nsym == MMA_ENC_AA ? MMA_AA_KB : mma_pb(db->mma_nsym, db->L) * db->mma_nsym;
+}
 
 // The encoding a db of window length L gets when `want` is requested (+-1 features need two spare
 // positions per feature block: L = 63 falls back to the 4-symbol one-hot operands).
-uint32_t mma_pick_encoding(uint32_t want, uint32_t L) {
+uint32_t mma_pick_encoding(uint32_t want, uint32_t L, int alphabet) {
+  // protein: the 4-class filter image is too permissive for loose bounds (random 20-aa windows sit at class
+  // distance ~15 of 20), so short protein windows get exact one-hot operands unless an ablation asks otherwise
+  if (alphabet == ALPHA_AA && mma_enc_ok(MMA_ENC_AA, L) && !getenv("SMAFA_MMA_NSYM")) return MMA_ENC_AA;
   if (want < 2 || want > 5) want = 3;
   return mma_enc_ok(want, L) ? want : 4;
 }
@@ -726,8 +764,8 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   if (db->L == 0 || db->L > 63 || n == 0) return SMAFA_OK;
   const uint32_t end = (uint32_t)(first + n);
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
-  launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0, nullptr,
-                      db->onehot, ctx->stream);
+  launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0,
+                      db->alphabet, nullptr, db->onehot, ctx->stream);
   return SMAFA_OK;
 }
 
@@ -766,7 +804,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   MmaParams P{};
   P.sp = p;
   P.need0 = std::max(0, (int)p.L - ctx->mma_bound0);  // the initial bound is uniform over the batch
-  launch_pack_operand(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, 1, P.need0, meta,
+  launch_pack_operand(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, 1, P.need0, db->alphabet, meta,
                       ctx->q_onehot, s);
   P.dump = dump;
   P.q_meta = meta;
@@ -797,6 +835,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   static const int epi = getenv("SMAFA_MMA_EPI") ? atoi(getenv("SMAFA_MMA_EPI")) : 8;
   static const bool pack16 = getenv("SMAFA_MMA_PACK16") ? atoi(getenv("SMAFA_MMA_PACK16")) != 0 : true;
   switch (db->mma_nsym) {
+    case MMA_ENC_AA: e = launch_mma<13, (int)MMA_ENC_AA, 2, 8, true, 1>(P, grid, s); break;
     case 5: e = wide ? launch_mma<10, 5, 3, 8, true, 1>(P, grid, s) : launch_mma<5, 5, 4, 8, true>(P, grid, s); break;
     case 4: e = wide ? launch_mma<8, 4, 2, 8, true>(P, grid, s) : launch_mma<4, 4, 4, 8, true>(P, grid, s); break;
     case 2: e = wide ? launch_mma<4, 2, 4, 8, true>(P, grid, s) : launch_mma<2, 2, 4, 8, true>(P, grid, s); break;

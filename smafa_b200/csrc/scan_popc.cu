@@ -41,7 +41,13 @@ __device__ __forceinline__ Planes<PW> load_row(const uint32_t *__restrict__ base
 }
 
 // Out-of-line slow path; returns the tightened bound (by value, so the bounds stay in registers).
+// For protein windows `d` is the distance of the 4-class filter image (a lower bound): the exact distance is
+// taken from the symbol words here.
 __device__ __noinline__ int popc_hit(const ScanParams *p, uint32_t q, uint32_t j, int d, int bound) {
+  if (p->alphabet != ALPHA_NUC) {
+    d = ref_distance(p->q_ref + (size_t)q * p->W, p->d_ref + (size_t)j * p->W, p->W, p->alphabet);
+    if (d > bound) return bound;
+  }
   emit_candidate(*p, q, j, d, bound);
   return bound;
 }
@@ -211,10 +217,75 @@ __global__ void __launch_bounds__(POPC_THREADS) bound_prepass_kernel(const __gri
   atomicMin(p.bound + q, best);
 }
 
+// The same estimator on the reference words (exact for every alphabet): used for protein windows, whose
+// planes hold the 4-class filter image -- plane distances there are lower bounds and would give bounds that
+// are too tight.  One block = 256 queries x the whole sample; tile = 256 windows x W words.
+template <int W>
+__global__ void __launch_bounds__(POPC_THREADS) bound_prepass_ref_kernel(const __grid_constant__ ScanParams p, uint32_t tile_stride) {
+  constexpr int HB = 66;
+  __shared__ uint64_t tile[POPC_TILE * W];
+  extern __shared__ uint16_t hist[];  // [HB][256], MODE_KTH only
+  const uint32_t tid = threadIdx.x, q = blockIdx.x * POPC_THREADS + tid;
+  const bool kth = p.mode == MODE_KTH;
+  uint64_t qw[W];
+  int best = -1;
+#pragma unroll
+  for (int x = 0; x < W; ++x) qw[x] = 0;
+  if (q < p.Q) {
+#pragma unroll
+    for (int x = 0; x < W; ++x) qw[x] = p.q_ref[(size_t)q * W + x];
+    best = __ldcg(p.bound + q);
+  }
+  if (kth)
+    for (int b = 0; b < HB; ++b) hist[b * POPC_THREADS + tid] = 0;
+  const uint32_t n_tiles = (p.d_end - p.d_begin + POPC_TILE - 1) / POPC_TILE;
+  for (uint32_t t = 0; t < n_tiles; t += tile_stride) {
+    const uint32_t t0 = p.d_begin + t * POPC_TILE;
+    const int nw = (int)min((uint32_t)POPC_TILE, p.d_end - t0);
+    __syncthreads();
+    for (int i = tid; i < nw * W; i += POPC_THREADS) tile[i] = p.d_ref[(size_t)t0 * W + i];
+    __syncthreads();
+    for (int w = 0; w < nw; ++w) {
+      const int dist = ref_distance(qw, tile + w * W, W, p.alphabet);
+      if (kth) {
+        if (dist <= best) hist[dist * POPC_THREADS + tid]++;  // a sample is < 65536 windows: no overflow
+      } else {
+        best = min(best, dist);
+      }
+    }
+  }
+  if (q >= p.Q) return;
+  if (kth) {
+    uint32_t cum = 0;
+    for (int t = 0; t <= best; ++t) {
+      cum += hist[t * POPC_THREADS + tid];
+      if (cum >= p.k) { best = t; break; }
+    }
+  }
+  atomicMin(p.bound + q, best);
+}
+
+template <int W>
+static void launch_prepass_ref(const ScanParams &p, uint32_t tile_stride, uint32_t blocks, size_t smem, cudaStream_t s) {
+  if (smem) cudaFuncSetAttribute(bound_prepass_ref_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bound_prepass_ref_kernel<W><<<blocks, POPC_THREADS, smem, s>>>(p, tile_stride);
+}
+
 int launch_bound_prepass(const ScanParams &p, uint32_t tile_stride, cudaStream_t s) {
   if (p.Q == 0 || p.d_end <= p.d_begin || p.L > 64) return 0;
   const uint32_t blocks = (p.Q + POPC_THREADS - 1) / POPC_THREADS;
   const size_t smem = p.mode == MODE_KTH ? (size_t)66 * POPC_THREADS * sizeof(uint16_t) : 0;
+  if (p.alphabet != ALPHA_NUC) {
+    switch (p.W) {
+      case 1: launch_prepass_ref<1>(p, tile_stride, blocks, smem, s); break;
+      case 2: launch_prepass_ref<2>(p, tile_stride, blocks, smem, s); break;
+      case 3: launch_prepass_ref<3>(p, tile_stride, blocks, smem, s); break;
+      case 4: launch_prepass_ref<4>(p, tile_stride, blocks, smem, s); break;
+      case 5: launch_prepass_ref<5>(p, tile_stride, blocks, smem, s); break;
+      default: launch_prepass_ref<6>(p, tile_stride, blocks, smem, s); break;
+    }
+    return 1;
+  }
   if (p.L <= 32) {
     if (smem) cudaFuncSetAttribute(bound_prepass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     bound_prepass_kernel<1><<<blocks, POPC_THREADS, smem, s>>>(p, tile_stride);
@@ -236,27 +307,27 @@ __global__ void __launch_bounds__(128) scan_generic_kernel(const ScanParams p, u
   const uint32_t w_begin = p.d_begin + ck * chunk;
   const uint32_t w_end = min(w_begin + chunk, p.d_end);
   for (uint32_t j = w_begin; j < w_end; ++j) {
-    int d = ref_distance(qw, p.d_ref + (size_t)j * p.W, p.W);
+    int d = ref_distance(qw, p.d_ref + (size_t)j * p.W, p.W, p.alphabet);
     if (d <= bound) emit_candidate(p, q, j, d, bound);
   }
 }
 
 // get_distances for parity/debug: out[q*D + j]
 __global__ void distances_kernel(const uint64_t *__restrict__ q_ref, uint32_t Q, const uint64_t *__restrict__ d_ref,
-                                 uint32_t D, uint32_t W, uint16_t *__restrict__ out) {
+                                 uint32_t D, uint32_t W, int alphabet, uint16_t *__restrict__ out) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t q = blockIdx.y;
   if (j >= D || q >= Q) return;
-  out[(size_t)q * D + j] = (uint16_t)ref_distance(q_ref + (size_t)q * W, d_ref + (size_t)j * W, W);
+  out[(size_t)q * D + j] = (uint16_t)ref_distance(q_ref + (size_t)q * W, d_ref + (size_t)j * W, W, alphabet);
 }
 
-void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W,
+void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, uint32_t D, uint32_t W, int alphabet,
                       uint16_t *out, cudaStream_t s) {
   if (Q == 0 || D == 0) return;
   for (uint32_t q0 = 0; q0 < Q; q0 += 32768) {
     uint32_t nq = min(Q - q0, 32768u);
     dim3 grid((D + 255) / 256, nq);
-    distances_kernel<<<grid, 256, 0, s>>>(q_ref + (size_t)q0 * W, nq, d_ref, D, W, out + (size_t)q0 * D);
+    distances_kernel<<<grid, 256, 0, s>>>(q_ref + (size_t)q0 * W, nq, d_ref, D, W, alphabet, out + (size_t)q0 * D);
   }
 }
 

@@ -73,7 +73,7 @@ struct EncodedInput {
 // Encodes records in order until one cannot be handled.  `expect_len` (0 = take the first
 // record's) is the window length every record must have; `mismatch` builds the panic text.
 template <class MismatchMsg>
-EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, MismatchMsg mismatch) {
+EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, int alphabet, MismatchMsg mismatch) {
   EncodedInput in;
   in.records = std::move(records);
   if (in.records.empty()) return in;
@@ -84,7 +84,7 @@ EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, Mismat
     const Record &r = in.records[i];
     std::vector<uint64_t> tmp(words_for_len(r.seq.size()) + 1);
     try {
-      encode_or_panic(r, tmp.data());  // encoding comes first in the reference (src/lib.rs:150,235)
+      encode_or_panic(r, tmp.data(), alphabet);  // encoding comes first in the reference (src/lib.rs:150,235)
     } catch (const Panic &e) {
       in.failed = true;
       in.failure = e.what();
@@ -106,24 +106,40 @@ EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, Mismat
 extern "C" uint8_t smafa_encode_symbol(uint8_t byte) { return SYMBOL_CODE[byte]; }
 
 extern "C" int smafa_encode_window(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos) {
-  if ((!seq && len) || !out_words) return SMAFA_E_INVALID;
-  return encode_window(seq, len, out_words, bad_pos) ? SMAFA_OK : SMAFA_E_PANIC;
+  return smafa_encode_window_alphabet(seq, len, out_words, bad_pos, SMAFA_ALPHABET_NUCLEOTIDE);
 }
 
 extern "C" int smafa_decode_window(const uint64_t *words, size_t len, char *out) {
-  return guarded([&] { decode_window(words, len, out); return (int)SMAFA_OK; });
+  return smafa_decode_window_alphabet(words, len, out, SMAFA_ALPHABET_NUCLEOTIDE);
+}
+
+extern "C" uint8_t smafa_encode_symbol_alphabet(uint8_t byte, int alphabet) {
+  return alphabet ? AA_SYMBOL_CODE[byte] : SYMBOL_CODE[byte];
+}
+
+extern "C" int smafa_encode_window_alphabet(const uint8_t *seq, size_t len, uint64_t *out_words, size_t *bad_pos, int alphabet) {
+  if ((!seq && len) || !out_words) return SMAFA_E_INVALID;
+  return encode_window(seq, len, out_words, bad_pos, alphabet) ? SMAFA_OK : SMAFA_E_PANIC;
+}
+
+extern "C" int smafa_decode_window_alphabet(const uint64_t *words, size_t len, char *out, int alphabet) {
+  return guarded([&] { decode_window(words, len, out, alphabet); return (int)SMAFA_OK; });
+}
+
+extern "C" int smafa_makedb_file(const char *subject_fasta, const char *db_path) {
+  return smafa_makedb_file_alphabet(subject_fasta, db_path, SMAFA_ALPHABET_NUCLEOTIDE);
 }
 
 // src/lib.rs:137-165
-extern "C" int smafa_makedb_file(const char *subject_fasta, const char *db_path) {
+extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char *db_path, int alphabet) {
   return guarded([&]() -> int {
     std::vector<Record> recs = read_fastx(subject_fasta);
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
-      encode_or_panic(recs[0], t.data());
+      encode_or_panic(recs[0], t.data(), alphabet);
       throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
     }
-    EncodedInput in = encode_all(std::move(recs), 0, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(recs), 0, alphabet, [](size_t got, uint32_t want) {
       return "WindowSet seq length is " + std::to_string(want) + ", got a new sequence of length " + std::to_string(got);
     });
     if (in.failed) throw Panic(in.failure);
@@ -167,10 +183,11 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
   smafa_db *dbh = nullptr;
   int rc = guarded([&]() -> int {
     if (!ctx) throw Panic("smafa_query_file needs a context (no CPU fallback)");
+    const int alphabet = ctx->alphabet;
     WindowDb db = parse_db(read_file(db_path));  // File::open(..)? -> Err, version gate -> panic
     std::vector<Record> recs = read_fastx(query_fasta);
     // get_distances checks the length only when the db is non-empty (src/lib.rs:72)
-    EncodedInput in = encode_all(std::move(recs), db.L, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(recs), db.L, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
@@ -198,7 +215,7 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
         n_hits = smafa_apply_limit_per_sequence(hits, n_hits, db.words.data(), db.W, 0, (uint32_t)limit_per_sequence);
       std::string dec(db.L, '\0');
       for (uint64_t i = 0; i < n_hits; ++i) {  // src/lib.rs:292,310
-        decode_window(db.words.data() + (size_t)hits[i].subject * db.W, db.L, dec.data());
+        decode_window(db.words.data() + (size_t)hits[i].subject * db.W, db.L, dec.data(), alphabet);
         out.put_u32(hits[i].query); out.buf.push_back('\t');
         out.put_u32(hits[i].subject); out.buf.push_back('\t');
         out.put_u32(hits[i].distance); out.buf.push_back('\t');
@@ -219,13 +236,14 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
 extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd) {
   return guarded([&]() -> int {
     if (!ctx) throw Panic("smafa_cluster_file needs a context (no CPU fallback)");
+    const int alphabet = ctx->alphabet;
     std::vector<Record> recs = read_fastx(input_fasta);
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
-      encode_or_panic(recs[0], t.data());
+      encode_or_panic(recs[0], t.data(), alphabet);
       throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
     }
-    EncodedInput in = encode_all(std::move(recs), 0, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(recs), 0, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
@@ -263,7 +281,7 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
     FdWriter out(out_fd);
     std::string dec(in.L, '\0');
     for (size_t u = 0; u < uniq.size(); ++u) {  // src/cluster.rs:79-84: raw input, decoded centroid
-      decode_window(uwords.data() + (size_t)cof[u] * in.W, in.L, dec.data());
+      decode_window(uwords.data() + (size_t)cof[u] * in.W, in.L, dec.data(), alphabet);
       out.buf.append(in.records[uniq[u]].seq); out.buf.push_back('\t');
       out.buf.append(dec); out.buf.push_back('\n');
       out.maybe_flush();

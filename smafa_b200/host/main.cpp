@@ -1,5 +1,6 @@
 // `smafa` command line of the B200 drop-in.  Same subcommands and flags as the reference binary
-// (src/main.rs:64-116); additive flags: --device N, --kernel {auto,popc,mma}.
+// (src/main.rs:64-116); additive flags: --device N, --kernel {auto,popc,mma}, --protein (amino-acid windows,
+// an extension: the reference only knows nucleotides).
 // Exit codes follow Rust: 0 ok, 101 for a reference panic, 1 for an Err from main, 2 usage.
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@ static int usage(const std::string &msg) {
           "  query    Search a database                         -d <FILE> -q <FILE> [--max-divergence <INT>]\n"
           "           [--max-num-hits <INT>] [--limit-per-sequence <INT>] [--device <INT>] [--kernel auto|popc|mma]\n"
           "  cluster  Cluster sequences by similarity           -i <FILE> -d <INT> [--device <INT>] [--kernel ..]\n"
+          "  (makedb/query/cluster: --protein treats the windows as amino acids -- an extension, not in the reference)\n"
           "  count    Print the number of reads/bases in a possibly gzipped FASTX file  -i <FILE>...\n",
           msg.c_str());
   return 2;
@@ -59,6 +61,7 @@ int main(int argc, char **argv) {
   std::vector<const char *> inputs;
   int64_t m = -1, k = -1, r = -1, device = 0;
   int kernel = SMAFA_KERNEL_AUTO;
+  int alphabet = SMAFA_ALPHABET_NUCLEOTIDE;
   for (; i < argc; ++i) {
     const char *a = argv[i];
     auto need = [&](int64_t *dst) {
@@ -77,6 +80,7 @@ int main(int argc, char **argv) {
     else if (is_query && is(a, nullptr, "--max-divergence")) { if (!need(&m)) return usage("invalid value for '--max-divergence <INT>'"); }
     else if (is_query && is(a, nullptr, "--max-num-hits")) { if (!need(&k)) return usage("invalid value for '--max-num-hits <INT>'"); }
     else if (is_query && is(a, nullptr, "--limit-per-sequence")) { if (!need(&r)) return usage("invalid value for '--limit-per-sequence <INT>'"); }
+    else if (!is_count && is(a, nullptr, "--protein")) alphabet = SMAFA_ALPHABET_PROTEIN;
     else if ((is_query || is_cluster) && is(a, nullptr, "--device")) { if (!need(&device)) return usage("invalid value for '--device <INT>'"); }
     else if ((is_query || is_cluster) && is(a, nullptr, "--kernel") && i + 1 < argc) {
       const std::string v = argv[++i];
@@ -88,7 +92,7 @@ int main(int argc, char **argv) {
   }
   if (is_makedb) {
     if (!input || !database) return usage("the following required arguments were not provided: --input <FILE> --database <FILE>");
-    return finish(smafa_makedb_file(input, database), nullptr);
+    return finish(smafa_makedb_file_alphabet(input, database, alphabet), nullptr);
   }
   if (is_count) {
     if (inputs.empty()) return usage("the following required arguments were not provided: --input <FILE>");
@@ -107,6 +111,7 @@ int main(int argc, char **argv) {
   smafa_ctx *ctx = nullptr;
   int rc = smafa_ctx_create(&ctx, (int)device, kernel);
   if (rc) return finish(rc, nullptr);
+  smafa_ctx_set_alphabet(ctx, alphabet);
   if (is_query) rc = smafa_query_file(ctx, database, query, m, k, r, 1);
   else rc = smafa_cluster_file(ctx, input, (uint32_t)m, 1);
   int code = finish(rc, ctx);

@@ -23,7 +23,31 @@ struct Lut {
   }
 };
 constexpr Lut kLut;
+
+struct AaLut {
+  uint8_t t[256];
+  constexpr AaLut() : t() {
+    for (int i = 0; i < 256; ++i) t[i] = 0;
+    const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+    for (int i = 0; aa[i]; ++i) { t[(int)aa[i]] = (uint8_t)(i + 1); t[(int)aa[i] + 32] = (uint8_t)(i + 1); }
+    const char *x = "XBZJUO";
+    for (int i = 0; x[i]; ++i) { t[(int)x[i]] = 21; t[(int)x[i] + 32] = 21; }
+    t['-'] = 22;
+    t['*'] = 23;
+  }
+};
+constexpr AaLut kAaLut;
 }  // namespace
+
+const uint8_t AA_SYMBOL_CODE[256] = {
+#define X4(i) kAaLut.t[i], kAaLut.t[i + 1], kAaLut.t[i + 2], kAaLut.t[i + 3]
+#define X16(i) X4(i), X4(i + 4), X4(i + 8), X4(i + 12)
+#define X64(i) X16(i), X16(i + 16), X16(i + 32), X16(i + 48)
+    X64(0), X64(64), X64(128), X64(192)
+#undef X64
+#undef X16
+#undef X4
+};
 
 const uint8_t SYMBOL_CODE[256] = {
 #define X4(i) kLut.t[i], kLut.t[i + 1], kLut.t[i + 2], kLut.t[i + 3]
@@ -35,13 +59,14 @@ const uint8_t SYMBOL_CODE[256] = {
 #undef X4
 };
 
-bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_pos) {
+bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_pos, int alphabet) {
   const uint32_t W = words_for_len(len);
+  const uint8_t *lut = alphabet ? AA_SYMBOL_CODE : SYMBOL_CODE;
   for (uint32_t w = 0; w < W; ++w) {
     const size_t base = (size_t)w * 12, n = len - base < 12 ? len - base : 12;
     uint64_t acc = 0;
     for (size_t i = 0; i < n; ++i) {
-      const uint8_t c = SYMBOL_CODE[seq[base + i]];
+      const uint8_t c = lut[seq[base + i]];
       if (!c) {
         if (bad_pos) *bad_pos = base + i;
         return false;
@@ -53,16 +78,19 @@ bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_po
   return true;
 }
 
-void encode_or_panic(const Record &r, uint64_t *out) {
+void encode_or_panic(const Record &r, uint64_t *out, int alphabet) {
   size_t bad = 0;
-  if (!encode_window(reinterpret_cast<const uint8_t *>(r.seq.data()), r.seq.size(), out, &bad))
-    throw Panic("Byte " + std::to_string((unsigned)(uint8_t)r.seq[bad]) +
-                " cannot be interpreted as nucleotide, in sequence \"" + r.id + "\" at position " +
+  if (!encode_window(reinterpret_cast<const uint8_t *>(r.seq.data()), r.seq.size(), out, &bad, alphabet))
+    throw Panic("Byte " + std::to_string((unsigned)(uint8_t)r.seq[bad]) + " cannot be interpreted as " +
+                (alphabet ? "amino acid" : "nucleotide") + ", in sequence \"" + r.id + "\" at position " +
                 std::to_string(bad));
 }
 
-void decode_window(const uint64_t *words, size_t len, char *out) {
-  static const char sym[32] = {0, 'N', 'T', 0, 'G', 0, 0, 0, 'C', 0, 0, 0, 0, 0, 0, 0, 'A'};
+void decode_window(const uint64_t *words, size_t len, char *out, int alphabet) {
+  static const char nuc[32] = {0, 'N', 'T', 0, 'G', 0, 0, 0, 'C', 0, 0, 0, 0, 0, 0, 0, 'A'};
+  static const char aa[32] = {0,   'A', 'C', 'D', 'E', 'F', 'G', 'H', 'I', 'K', 'L', 'M',
+                              'N', 'P', 'Q', 'R', 'S', 'T', 'V', 'W', 'Y', 'X', '-', '*'};
+  const char *sym = alphabet ? aa : nuc;
   for (size_t i = 0; i < len; ++i) {
     const unsigned b = (unsigned)(words[i / 12] >> (5 * (i % 12))) & 31u;
     const char c = sym[b];

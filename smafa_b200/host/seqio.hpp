@@ -30,11 +30,15 @@ struct Record {
 std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open = false);
 
 extern const uint8_t SYMBOL_CODE[256];  // src/lib.rs:167-184; 0 = not a nucleotide
+// Protein extension (not in the reference): symbol numbers 1..20 = ACDEFGHIKLMNPQRSTVWY,
+// 21 = X (also B, Z, J, U, O), 22 = '-', 23 = '*'; lower case accepted; 0 = not an amino-acid symbol.
+extern const uint8_t AA_SYMBOL_CODE[256];
 inline uint32_t words_for_len(size_t len) { return (uint32_t)((len + 11) / 12); }
+// alphabet: 0 = nucleotide (the reference's one-hot codes), 1 = protein (symbol numbers).
 // Returns false and sets *bad_pos at the first byte without a code.
-bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_pos);
-void encode_or_panic(const Record &r, uint64_t *out);  // panic text of src/lib.rs:38-41
-void decode_window(const uint64_t *words, size_t len, char *out);  // src/lib.rs:113-135
+bool encode_window(const uint8_t *seq, size_t len, uint64_t *out, size_t *bad_pos, int alphabet = 0);
+void encode_or_panic(const Record &r, uint64_t *out, int alphabet = 0);  // panic text of src/lib.rs:38-41
+void decode_window(const uint64_t *words, size_t len, char *out, int alphabet = 0);  // src/lib.rs:113-135
 
 struct WindowDb {
   std::vector<uint64_t> words;  // [n][W]

@@ -97,3 +97,54 @@ def random_symbols(n, L, seed, p_n=0.05):
     sym = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
     sym[rng.random((n, L)) < p_n] = 4
     return sym
+
+
+# ---- protein windows (configs[3]; an extension of this build: the reference has no amino-acid mode) ----
+SEED_PROTEIN = 0x5AFA0004
+_AA_ASCII = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX-*", dtype=np.uint8)  # symbol index s -> byte; number = s + 1
+
+
+def pack_symbols_aa(sym):
+    """uint8 [n, L] protein symbol indices (0..19 amino acids, 20 = X, 21 = '-', 22 = '*') -> uint64 words
+    holding the symbol NUMBER (index + 1) in the same 5-bit groups as the nucleotide layout."""
+    n, L = sym.shape
+    out = np.zeros((n, words_for_len(L)), dtype=np.uint64)
+    codes = sym.astype(np.uint64) + np.uint64(1)
+    for p in range(L):
+        out[:, p // 12] |= codes[:, p] << np.uint64(5 * (p % 12))
+    return out
+
+
+def to_ascii_aa(sym):
+    return [row.tobytes() for row in _AA_ASCII[sym]]
+
+
+def _mutate_aa(rng, base, max_subs, noise):
+    n, L = base.shape
+    out = base.copy()
+    s = rng.integers(0, max_subs + 1, size=n)
+    for j in range(max_subs):
+        rows = np.nonzero(s > j)[0]
+        if rows.size == 0:
+            break
+        pos = rng.integers(0, L, size=rows.size)
+        shift = rng.integers(1, 20, size=rows.size).astype(np.uint8)
+        out[rows, pos] = (base[rows, pos] + shift) % 20
+    if noise > 0:  # X / gap / stop noise, like the N/gap noise of the nucleotide generator
+        hit = rng.random(out.shape) < noise
+        out[hit] = rng.integers(20, 23, size=int(hit.sum()), dtype=np.uint8)
+    return out
+
+
+def make_db_aa(D, L=20, seed=SEED_PROTEIN, family=16, max_subs=4, noise=0.01):
+    """Protein analogue of make_db (same family construction over 20 letters, s ~ U{0..4})."""
+    rng = np.random.default_rng(seed)
+    R = max(1, D // family)
+    roots = rng.integers(0, 20, size=(R, L), dtype=np.uint8)
+    return _mutate_aa(rng, roots[np.arange(D) % R], max_subs, noise)
+
+
+def make_queries_aa(db_sym, Q, seed=SEED_PROTEIN + 1, max_subs=5, noise=0.01):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, db_sym.shape[0], size=Q)
+    return _mutate_aa(rng, db_sym[src], max_subs, noise)
