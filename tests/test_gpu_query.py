@@ -318,3 +318,37 @@ def test_config2_scale_subsample_and_properties(ctx, kernel):
     sub = self_hits[self_hits[:, 0] < 40]
     assert sub.shape == want.shape and (sub == want).all()
     d.close()
+
+
+# ---- BASELINE config 3 at full size on ONE GPU: 1M queries x 10M windows (the north-star target shape) ----
+
+def test_config3_full_size_single_gpu(ctx):
+    """1 M x 10 M = 10^13 comparisons through smafa_query (default kernel), --max-divergence 5.  The oracle needs
+    ~10^5 core-seconds for the whole job, so parity is checked bit-exactly on a query subsample spread over the
+    whole batch and, for every one of the rows, through properties that do not depend on the size."""
+    L, D, Q = 60, 10_000_000, 1_000_000
+    db_sym = synth.make_db(D, L=L)
+    q_sym = synth.make_queries(db_sym, Q)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    del db_sym, q_sym
+    ctx.set_kernel("auto")
+    d = ctx.upload(db, L)
+    got, st = ctx.query(d, q, L, max_divergence=5, return_stats=True)
+    assert st["pairs"] == Q * D and st["kernel_used"] == 2
+    # (1) bit-exact on 96 queries taken from the start, the middle and the end of the batch
+    pick = np.concatenate([np.arange(32), Q // 2 + np.arange(32), Q - 32 + np.arange(32)])
+    want = c_oracle.query(db, L, q[pick], L, 5, None, None, threads=os.cpu_count() or 1)
+    want[:, 0] = pick[want[:, 0]]
+    sub = got[np.isin(got[:, 0], pick)]
+    assert sub.shape == want.shape and (sub == want).all()
+    # (2) properties over all rows: print order, bound, one distance per query, ascending subjects within a query,
+    # and every reported distance re-derived from the encodings
+    assert (np.diff(got[:, 0].astype(np.int64)) >= 0).all()
+    assert (got[:, 2] <= 5).all()
+    same_q = got[1:, 0] == got[:-1, 0]
+    assert (got[1:, 2][same_q] == got[:-1, 2][same_q]).all()
+    assert (got[1:, 1][same_q] > got[:-1, 1][same_q]).all()
+    x = np.bitwise_count(db[got[:, 1]] ^ q[got[:, 0]]).sum(axis=1) // 2
+    assert (x == got[:, 2]).all()
+    assert got.shape[0] > Q // 4  # about half of the queries sit within 5 of their source window
+    d.close()
