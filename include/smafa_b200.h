@@ -180,6 +180,10 @@ int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fast
                      int out_fd);
 int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd);
 int smafa_count_files(const char *const *paths, size_t n_paths, int out_fd);
+/* Loads a db file into host words (src/lib.rs:206-218: File::open, version gate, postcard decode) -- the
+ * LEB128 stream is decoded on all host threads.  *words ([n][W], reference bit layout) is released with
+ * smafa_free(); window_len 0 == None (empty db).  No GPU needed. */
+int smafa_db_file_load(const char *db_path, uint64_t **words, uint64_t *n, uint32_t *W, uint32_t *window_len);
 /* Opens a db file and applies the version gate of src/lib.rs:208-217 (no GPU needed). */
 int smafa_db_file_check(const char *db_path);
 

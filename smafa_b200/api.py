@@ -94,6 +94,7 @@ def load_library():
     l.smafa_cluster_file.argtypes = [vp, C.c_char_p, u32, C.c_int]
     l.smafa_count_files.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, C.c_int]
     l.smafa_db_file_check.argtypes = [C.c_char_p]
+    l.smafa_db_file_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
     l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
     l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
     l.smafa_db_mma_k.restype = u32
@@ -309,6 +310,20 @@ class Db:
 
 
 # ---- file-level mirror of the reference's public functions ---------------------------------
+
+def load_db_file(db_path):
+    """smafa::query's db load (reference src/lib.rs:206-218) -> (uint64 [n, W] words, window length or None)."""
+    l = load_library()
+    words = C.POINTER(C.c_uint64)()
+    n, W, L = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+    rc = l.smafa_db_file_load(os.fsencode(db_path), C.byref(words), C.byref(n), C.byref(W), C.byref(L))
+    if rc:
+        _raise(rc)
+    arr = (np.ctypeslib.as_array(words, shape=(n.value, W.value)).copy() if n.value * W.value
+           else np.zeros((n.value, W.value), dtype=np.uint64))
+    l.smafa_free(words)
+    return arr, (L.value or None)
+
 
 def makedb(subject_fasta, db_path, protein=False):
     """smafa::makedb (reference src/lib.rs:137-165).  Host only.  protein=True: the amino-acid extension."""

@@ -4,6 +4,10 @@
 // C ABI (smafa_query / smafa_cluster) to the B200 kernels.  There is no CPU fallback for it.
 #include <unistd.h>
 
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -61,6 +65,18 @@ struct FdWriter {
   }
 };
 
+// SMAFA_TIMING=1: per-stage wall times of the file-level calls on stderr (measurement aid, not compared).
+struct StageTimer {
+  bool on = getenv("SMAFA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[smafa timing] %-28s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 struct EncodedInput {
   std::vector<Record> records;
   std::vector<uint64_t> words;  // [n_ok][W]
@@ -80,24 +96,36 @@ EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, int al
   in.L = expect_len ? expect_len : (uint32_t)in.records[0].seq.size();
   in.W = words_for_len(in.L);
   in.words.resize(in.records.size() * (size_t)in.W);
-  for (size_t i = 0; i < in.records.size(); ++i) {
-    const Record &r = in.records[i];
-    std::vector<uint64_t> tmp(words_for_len(r.seq.size()) + 1);
-    try {
-      encode_or_panic(r, tmp.data(), alphabet);  // encoding comes first in the reference (src/lib.rs:150,235)
-    } catch (const Panic &e) {
-      in.failed = true;
-      in.failure = e.what();
-      break;
+  // Records are independent, so they are encoded on all host threads; the reference stops at
+  // the first record it cannot handle, which is the lowest failing index over all chunks.
+  struct Fail { size_t index = SIZE_MAX; std::string text; };
+  const unsigned T = host_threads();
+  std::vector<Fail> fails(T);
+  parallel_chunks(in.records.size(), 16384, [&](unsigned t, size_t lo, size_t hi) {
+    std::vector<uint64_t> tmp;
+    for (size_t i = lo; i < hi; ++i) {
+      const Record &r = in.records[i];
+      tmp.assign(words_for_len(r.seq.size()) + 1, 0);
+      try {
+        encode_or_panic(r, tmp.data(), alphabet);  // encoding comes first in the reference (src/lib.rs:150,235)
+      } catch (const Panic &e) {
+        fails[t] = Fail{i, e.what()};
+        return;
+      }
+      if (r.seq.size() != in.L) {
+        fails[t] = Fail{i, mismatch(r.seq.size(), in.L)};
+        return;
+      }
+      memcpy(in.words.data() + i * in.W, tmp.data(), in.W * sizeof(uint64_t));
     }
-    if (r.seq.size() != in.L) {
+  });
+  in.n_ok = in.records.size();
+  for (const Fail &f : fails)
+    if (f.index < in.n_ok) {
+      in.n_ok = f.index;
       in.failed = true;
-      in.failure = mismatch(r.seq.size(), in.L);
-      break;
+      in.failure = f.text;
     }
-    memcpy(in.words.data() + i * in.W, tmp.data(), in.W * sizeof(uint64_t));
-    in.n_ok = i + 1;
-  }
   return in;
 }
 
@@ -133,7 +161,9 @@ extern "C" int smafa_makedb_file(const char *subject_fasta, const char *db_path)
 // src/lib.rs:137-165
 extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char *db_path, int alphabet) {
   return guarded([&]() -> int {
+    StageTimer tm;
     std::vector<Record> recs = read_fastx(subject_fasta);
+    tm.lap("makedb: read FASTX");
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
       encode_or_panic(recs[0], t.data(), alphabet);
@@ -142,6 +172,7 @@ extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char 
     EncodedInput in = encode_all(std::move(recs), 0, alphabet, [](size_t got, uint32_t want) {
       return "WindowSet seq length is " + std::to_string(want) + ", got a new sequence of length " + std::to_string(got);
     });
+    tm.lap("makedb: encode");
     if (in.failed) throw Panic(in.failure);
     WindowDb db;
     db.n = in.n_ok;
@@ -149,11 +180,30 @@ extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char 
     db.L = in.L;
     db.words = std::move(in.words);
     const std::vector<uint8_t> bytes = serialize_db(db);
+    tm.lap("makedb: serialize");
     FILE *f = fopen(db_path, "wb");
     if (!f) throw IoError(std::string("cannot create ") + db_path);
     const size_t w = fwrite(bytes.data(), 1, bytes.size(), f);
     fclose(f);
     if (w != bytes.size()) throw IoError("short write");
+    tm.lap("makedb: write");
+    return SMAFA_OK;
+  });
+}
+
+// src/lib.rs:206-218
+extern "C" int smafa_db_file_load(const char *db_path, uint64_t **words, uint64_t *n, uint32_t *W, uint32_t *window_len) {
+  if (!db_path || !words || !n || !W || !window_len) return SMAFA_E_INVALID;
+  *words = nullptr;
+  return guarded([&]() -> int {
+    WindowDb db = parse_db(read_file(db_path));
+    uint64_t *out = (uint64_t *)malloc(std::max<size_t>(1, db.words.size()) * sizeof(uint64_t));
+    if (!out) throw std::bad_alloc();
+    memcpy(out, db.words.data(), db.words.size() * sizeof(uint64_t));
+    *words = out;
+    *n = db.n;
+    *W = db.W;
+    *window_len = db.L;
     return SMAFA_OK;
   });
 }
@@ -184,18 +234,23 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
   int rc = guarded([&]() -> int {
     if (!ctx) throw Panic("smafa_query_file needs a context (no CPU fallback)");
     const int alphabet = ctx->alphabet;
+    StageTimer tm;
     WindowDb db = parse_db(read_file(db_path));  // File::open(..)? -> Err, version gate -> panic
+    tm.lap("query: read + decode db");
     std::vector<Record> recs = read_fastx(query_fasta);
+    tm.lap("query: read FASTX");
     // get_distances checks the length only when the db is non-empty (src/lib.rs:72)
     EncodedInput in = encode_all(std::move(recs), db.L, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
+    tm.lap("query: encode");
     const bool mode_b = max_num_hits >= 0 && max_num_hits != 1;  // src/lib.rs:224
     FdWriter out(out_fd);
     if (in.n_ok > 0) {
       int r = smafa_db_upload(ctx, db.words.data(), db.n, db.L, 0, &dbh);
       if (r) return r;
+      tm.lap("query: db upload + re-pack");
       // Mode A with --limit-per-sequence panics right after the first min() (src/lib.rs:298-303)
       const uint64_t nq = (!mode_b && limit_per_sequence >= 0 && db.n > 0) ? 0 : in.n_ok;
       smafa_hit *hits = nullptr;
@@ -206,6 +261,7 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
         smafa_set_global_error(smafa_last_error(ctx));
         return r;
       }
+      tm.lap("query: scan + selection");
       if (nq == 0) {
         smafa_free(hits);
         throw Panic("limit_per_sequence is implemented unless max_num_hits > 1. It can be implemented by analogy, "
@@ -213,15 +269,30 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
       }
       if (mode_b && limit_per_sequence >= 0)
         n_hits = smafa_apply_limit_per_sequence(hits, n_hits, db.words.data(), db.W, 0, (uint32_t)limit_per_sequence);
-      std::string dec(db.L, '\0');
-      for (uint64_t i = 0; i < n_hits; ++i) {  // src/lib.rs:292,310
-        decode_window(db.words.data() + (size_t)hits[i].subject * db.W, db.L, dec.data(), alphabet);
-        out.put_u32(hits[i].query); out.buf.push_back('\t');
-        out.put_u32(hits[i].subject); out.buf.push_back('\t');
-        out.put_u32(hits[i].distance); out.buf.push_back('\t');
-        out.buf.append(dec); out.buf.push_back('\n');
-        out.maybe_flush();
+      // src/lib.rs:292,310: "query\tsubject\tdistance\tdecoded subject\n".  Lines are formatted on all host
+      // threads into per-chunk buffers and written in order.
+      const unsigned T = n_hits >= 65536 ? host_threads() : 1;
+      std::vector<std::string> parts(T);
+      parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; ++t) {
+          FdWriter w(-1);
+          w.buf.reserve((size_t)(n_hits / T + 1) * (db.L + 24));
+          std::string dec(db.L, '\0');
+          for (uint64_t i = n_hits * t / T; i < n_hits * (t + 1) / T; ++i) {
+            decode_window(db.words.data() + (size_t)hits[i].subject * db.W, db.L, dec.data(), alphabet);
+            w.put_u32(hits[i].query); w.buf.push_back('\t');
+            w.put_u32(hits[i].subject); w.buf.push_back('\t');
+            w.put_u32(hits[i].distance); w.buf.push_back('\t');
+            w.buf.append(dec); w.buf.push_back('\n');
+          }
+          parts[t] = std::move(w.buf);
+        }
+      });
+      for (std::string &part : parts) {
+        out.buf = std::move(part);
+        out.flush();
       }
+      tm.lap("query: format + write TSV");
       smafa_free(hits);
       out.flush();
     }
@@ -237,7 +308,9 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
   return guarded([&]() -> int {
     if (!ctx) throw Panic("smafa_cluster_file needs a context (no CPU fallback)");
     const int alphabet = ctx->alphabet;
+    StageTimer tm;
     std::vector<Record> recs = read_fastx(input_fasta);
+    tm.lap("cluster: read FASTX");
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
       encode_or_panic(recs[0], t.data(), alphabet);
@@ -272,12 +345,14 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
         uwords.insert(uwords.end(), k.w, k.w + in.W);
       }
     }
+    tm.lap("cluster: encode + de-duplicate");
     std::vector<uint32_t> cof(uniq.size());
     uint64_t n_centroids = 0;
     if (!uniq.empty()) {
       int r = smafa_cluster(ctx, uwords.data(), uniq.size(), in.L, max_divergence, cof.data(), &n_centroids, nullptr, nullptr);
       if (r) { smafa_set_global_error(smafa_last_error(ctx)); return r; }
     }
+    tm.lap("cluster: greedy (GPU distances)");
     FdWriter out(out_fd);
     std::string dec(in.L, '\0');
     for (size_t u = 0; u < uniq.size(); ++u) {  // src/cluster.rs:79-84: raw input, decoded centroid
@@ -287,6 +362,7 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
       out.maybe_flush();
     }
     out.flush();
+    tm.lap("cluster: format + write");
     if (in.failed) throw Panic(in.failure);
     return SMAFA_OK;
   });

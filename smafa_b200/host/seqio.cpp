@@ -2,9 +2,15 @@
 
 #include <zlib.h>
 
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace smafa_host {
 
@@ -99,12 +105,45 @@ void decode_window(const uint64_t *words, size_t len, char *out, int alphabet) {
   }
 }
 
+unsigned host_threads() {
+  static const unsigned n = [] {
+    if (const char *e = getenv("SMAFA_HOST_THREADS")) {
+      const int v = atoi(e);
+      if (v >= 1) return (unsigned)std::min(v, 256);
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return std::min(std::max(hc, 1u), 32u);
+  }();
+  return n;
+}
+
+void parallel_chunks(size_t n, size_t min_per_thread, const std::function<void(unsigned, size_t, size_t)> &fn) {
+  unsigned T = (unsigned)std::min<size_t>(host_threads(), std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread)));
+  if (T <= 1) { fn(0, 0, n); return; }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(T);
+  for (unsigned t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      try { fn(t, n * t / T, n * (t + 1) / T); } catch (...) { err[t] = std::current_exception(); }
+    });
+  for (auto &x : th) x.join();
+  for (auto &e : err)
+    if (e) std::rethrow_exception(e);  // the lowest-numbered chunk's failure, i.e. the first in input order
+}
+
 std::vector<uint8_t> read_file(const std::string &path) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f)
     throw IoError("Os { code: " + std::to_string(errno) + ", kind: NotFound, message: \"" + strerror(errno) + "\" }");
   std::vector<uint8_t> buf;
-  uint8_t tmp[1 << 16];
+  struct stat st;
+  if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {  // one allocation, one read
+    buf.resize((size_t)st.st_size);
+    size_t got = 0, r;
+    while (got < buf.size() && (r = fread(buf.data() + got, 1, buf.size() - got, f)) > 0) got += r;
+    buf.resize(got);
+  }
+  uint8_t tmp[1 << 16];  // pipes, or a file that grew
   size_t r;
   while ((r = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + r);
   fclose(f);
@@ -118,7 +157,10 @@ static std::vector<uint8_t> read_maybe_gz(const std::string &path, bool io_error
     if (io_error_on_open) throw IoError(msg);
     throw Panic("valid path/file of input: " + msg);
   }
+  uint8_t magic[2] = {0, 0};
+  const size_t got = fread(magic, 1, 2, probe);
   fclose(probe);
+  if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) return read_file(path);  // not gzip: no zlib pass
   gzFile g = gzopen(path.c_str(), "rb");
   if (!g) throw IoError("cannot open " + path);
   gzbuffer(g, 1 << 20);
@@ -134,9 +176,22 @@ static std::vector<uint8_t> read_maybe_gz(const std::string &path, bool io_error
   return buf;
 }
 
+// Appends b[0, n) without line endings, one memchr + append per line.
 static void append_stripped(std::string &dst, const uint8_t *b, size_t n) {
-  for (size_t i = 0; i < n; ++i)
-    if (b[i] != '\n' && b[i] != '\r') dst.push_back((char)b[i]);
+  size_t p = 0;
+  while (p < n) {
+    const void *nl = memchr(b + p, '\n', n - p);
+    size_t e = nl ? (size_t)((const uint8_t *)nl - b) : n;
+    size_t le = e;
+    while (le > p && b[le - 1] == '\r') --le;
+    if (memchr(b + p, '\r', le - p) == nullptr) {
+      dst.append(reinterpret_cast<const char *>(b + p), le - p);
+    } else {  // stray carriage returns inside a line: the slow, exact way
+      for (size_t i = p; i < le; ++i)
+        if (b[i] != '\r') dst.push_back((char)b[i]);
+    }
+    p = e + 1;
+  }
 }
 
 std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open) {
@@ -147,27 +202,61 @@ std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open) {
   if (n == 0) throw Panic("valid path/file: EmptyFile");
   size_t p = 0;
   if (b[0] == '>') {
-    while (p < n) {
-      if (b[p] != '>') throw Panic("valid record: InvalidStart");
-      size_t he = p + 1;
-      while (he < n && b[he] != '\n') ++he;
-      size_t idn = he - (p + 1);
-      if (idn && b[p + idn] == '\r') --idn;
-      Record r;
-      r.id.assign(reinterpret_cast<const char *>(b + p + 1), idn);
-      size_t ss = he < n ? he + 1 : n, se = ss;
-      while (se < n) {  // next '>' at the start of a line ends the record
-        const void *gt = memchr(b + se, '>', n - se);
-        if (!gt) { se = n; break; }
-        se = (const uint8_t *)gt - b;
-        if (se == ss || b[se - 1] == '\n') break;
-        ++se;
+    // Records of [lo, hi): lo is a record start ('>' at the start of a line), hi is the next chunk's start.
+    auto parse_range = [&](size_t lo, size_t hi, std::vector<Record> &dst) {
+      size_t p = lo;
+      while (p < hi) {
+        if (b[p] != '>') throw Panic("valid record: InvalidStart");
+        size_t he = p + 1;
+        const void *nl = memchr(b + he, '\n', n - he);
+        he = nl ? (size_t)((const uint8_t *)nl - b) : n;
+        size_t idn = he - (p + 1);
+        if (idn && b[p + idn] == '\r') --idn;
+        Record r;
+        r.id.assign(reinterpret_cast<const char *>(b + p + 1), idn);
+        size_t ss = he < n ? he + 1 : n, se = ss;
+        while (se < n) {  // next '>' at the start of a line ends the record
+          const void *gt = memchr(b + se, '>', n - se);
+          if (!gt) { se = n; break; }
+          se = (const uint8_t *)gt - b;
+          if (se == ss || b[se - 1] == '\n') break;
+          ++se;
+        }
+        r.seq.reserve(se - ss);
+        append_stripped(r.seq, b + ss, se - ss);
+        dst.push_back(std::move(r));
+        p = se;
       }
-      r.seq.reserve(se - ss);
-      append_stripped(r.seq, b + ss, se - ss);
-      out.push_back(std::move(r));
-      p = se;
+    };
+    // chunk boundaries = the first record start at or after the nominal split points
+    const unsigned T = n >= (8u << 20) ? host_threads() : 1;
+    std::vector<size_t> cut(T + 1, n);
+    cut[0] = 0;
+    for (unsigned t = 1; t < T; ++t) {
+      size_t q = std::max(cut[t - 1], n * t / T);
+      while (q < n) {
+        const void *gt = memchr(b + q, '>', n - q);
+        if (!gt) { q = n; break; }
+        q = (const uint8_t *)gt - b;
+        if (q == 0 || b[q - 1] == '\n') break;
+        ++q;
+      }
+      cut[t] = q;
     }
+    if (T == 1) {
+      parse_range(0, n, out);
+    } else {
+      std::vector<std::vector<Record>> parts(T);
+      parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; ++t) parse_range(cut[t], cut[t + 1], parts[t]);
+      });
+      size_t total = 0;
+      for (auto &v : parts) total += v.size();
+      out.reserve(total);
+      for (auto &v : parts)
+        for (auto &r : v) out.push_back(std::move(r));
+    }
+    p = n;
   } else if (b[0] == '@') {
     while (p < n) {
       if (b[p] == '\n' || b[p] == '\r') { ++p; continue; }
@@ -230,6 +319,97 @@ struct Cursor {
 };
 }  // namespace
 
+// Sequential decode of the window list (also the arbiter of every malformed file: the parallel path below
+// falls back to it whenever anything looks off, so error behaviour is that of one straight pass).
+static void parse_body_sequential(Cursor &c, WindowDb &db) {
+  for (uint64_t i = 0; i < db.n; ++i) {
+    const uint64_t w = c.varint(10);
+    if (i == 0) {
+      db.W = (uint32_t)w;
+      db.words.resize(db.n * db.W);
+    } else if (w != db.W) {
+      throw IoError("db file holds windows of different word counts");
+    }
+    uint64_t *dst = db.words.data() + i * db.W;
+    for (uint32_t j = 0; j < db.W; ++j) dst[j] = c.varint(10);
+  }
+}
+
+// Parallel decode.  A LEB128 stream can be entered at any byte that follows a terminator
+// (MSB clear), so the body is cut into byte ranges that start on varint boundaries; a first pass counts the
+// terminators of every range (= varints in it), the prefix sum gives each range the index of its first
+// varint, and since every window is exactly 1 + W varints (inner Vec length, then the words) that index maps
+// to (window, slot) directly.  Returns false when the stream does not have that regular shape.
+static bool parse_body_parallel(Cursor &c, WindowDb &db) {
+  const uint8_t *b = c.b;
+  const size_t body = c.p, n = c.n;
+  Cursor probe{b, n, body};
+  const uint64_t W = probe.varint(10);
+  if (W == 0 || W > 512) return false;
+  const uint64_t V = db.n * (W + 1);  // varints in the body
+  const unsigned T = host_threads();
+  if (T <= 1 || n - body < (size_t)T * 4096) return false;
+  std::vector<size_t> start(T + 1, n);
+  start[0] = body;
+  for (unsigned t = 1; t < T; ++t) {
+    size_t q = std::max(start[t - 1], body + (n - body) * t / T);
+    while (q < n && q > body && (b[q - 1] & 0x80)) ++q;  // advance to a byte that follows a terminator
+    start[t] = q;
+  }
+  std::vector<uint64_t> count(T + 1, 0);
+  parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+    for (size_t t = t0; t < t1; ++t) {
+      uint64_t cnt = 0;
+      const uint8_t *p = b + start[t], *e = b + start[t + 1];
+      for (; p + 8 <= e; p += 8) {
+        uint64_t x;
+        memcpy(&x, p, 8);
+        cnt += 8 - (uint64_t)__builtin_popcountll(x & 0x8080808080808080ull);
+      }
+      for (; p < e; ++p) cnt += !(*p & 0x80);
+      count[t + 1] = cnt;
+    }
+  });
+  for (unsigned t = 0; t < T; ++t) count[t + 1] += count[t];
+  if (count[T] < V + 1) return false;  // truncated (the Option tag after the body is one more terminator)
+  db.W = (uint32_t)W;
+  db.words.resize(db.n * W);
+  std::atomic<bool> bad{false};
+  std::vector<size_t> body_end(T, 0);
+  parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+    for (size_t t = t0; t < t1; ++t) {
+      uint64_t idx = count[t];
+      if (idx >= V) continue;
+      uint64_t win = idx / (W + 1), slot = idx % (W + 1);
+      Cursor cur{b, start[t + 1], start[t]};
+      while (cur.p < start[t + 1] && idx < V) {
+        uint64_t v = 0;
+        int i = 0;
+        for (;; ++i) {
+          if (i == 10 || cur.p >= n) { bad = true; return; }
+          const uint8_t ch = b[cur.p++];
+          v |= (uint64_t)(ch & 0x7f) << (7 * i);
+          if (!(ch & 0x80)) break;
+        }
+        if (slot == 0) {
+          if (v != W) { bad = true; return; }
+        } else {
+          db.words[win * W + slot - 1] = v;
+        }
+        if (++slot == W + 1) { slot = 0; ++win; }
+        ++idx;
+      }
+      if (idx == V) body_end[t] = cur.p;
+    }
+  });
+  if (bad) return false;
+  size_t end = 0;
+  for (unsigned t = 0; t < T; ++t) end = std::max(end, body_end[t]);
+  if (end == 0) return false;
+  c.p = end;
+  return true;
+}
+
 WindowDb parse_db(const std::vector<uint8_t> &bytes) {
   if (bytes.size() < 4)  // &buffer[0..4], src/lib.rs:214
     throw Panic("range end index 4 out of range for slice of length " + std::to_string(bytes.size()));
@@ -243,16 +423,11 @@ WindowDb parse_db(const std::vector<uint8_t> &bytes) {
   c.varint(5);
   WindowDb db;
   db.n = c.varint(10);
-  for (uint64_t i = 0; i < db.n; ++i) {
-    const uint64_t w = c.varint(10);
-    if (i == 0) {
-      db.W = (uint32_t)w;
-      db.words.resize(db.n * db.W);
-    } else if (w != db.W) {
-      throw IoError("db file holds windows of different word counts");
-    }
-    uint64_t *dst = db.words.data() + i * db.W;
-    for (uint32_t j = 0; j < db.W; ++j) dst[j] = c.varint(10);
+  const size_t body = c.p;
+  if (db.n < 65536 || db.n > bytes.size() || !parse_body_parallel(c, db)) {
+    c.p = body;
+    db.words.clear();
+    parse_body_sequential(c, db);
   }
   if (c.p >= c.n) throw IoError("DeserializeUnexpectedEnd");
   const uint8_t tag = c.b[c.p++];

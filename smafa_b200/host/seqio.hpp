@@ -3,6 +3,7 @@
 // decode helpers of the reference (src/lib.rs:29-52,113-135,137-165,167-196,206-218).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -17,6 +18,12 @@ struct Panic : std::runtime_error {
 struct IoError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+
+// Host worker threads for the ingest paths (db decode, FASTA parse, window encoding): the hardware concurrency,
+// capped at 32; SMAFA_HOST_THREADS overrides.  The reference is single-threaded; results do not depend on it.
+unsigned host_threads();
+// Runs fn(thread, begin, end) over [0, n) split into contiguous chunks; rethrows the failure of the lowest chunk.
+void parallel_chunks(size_t n, size_t min_per_thread, const std::function<void(unsigned, size_t, size_t)> &fn);
 
 constexpr uint32_t DB_VERSION = 2;  // CURRENT_DB_VERSION, src/lib.rs:18
 
