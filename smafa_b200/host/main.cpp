@@ -2,6 +2,7 @@
 // (src/main.rs:64-116); additive flags: --device N, --kernel {auto,popc,mma}, --protein (amino-acid windows,
 // an extension: the reference only knows nucleotides).
 // Exit codes follow Rust: 0 ok, 101 for a reference panic, 1 for an Err from main, 2 usage.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,13 +109,24 @@ int main(int argc, char **argv) {
     int pre = smafa_db_file_check(database);
     if (pre) return finish(pre, nullptr);
   }
+  const bool timing = getenv("SMAFA_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[smafa timing] %-28s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+    t0 = now;
+  };
   smafa_ctx *ctx = nullptr;
   int rc = smafa_ctx_create(&ctx, (int)device, kernel);
   if (rc) return finish(rc, nullptr);
+  lap("CUDA init + context");
   smafa_ctx_set_alphabet(ctx, alphabet);
   if (is_query) rc = smafa_query_file(ctx, database, query, m, k, r, 1);
   else rc = smafa_cluster_file(ctx, input, (uint32_t)m, 1);
+  lap(is_query ? "query (all stages above)" : "cluster (all stages above)");
   int code = finish(rc, ctx);
   smafa_ctx_destroy(ctx);
+  lap("context teardown");
   return code;
 }
