@@ -792,13 +792,14 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
   const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N * sizeof(int16_t);  // operand tiles + q_meta
   if (ctx->q_onehot_cap < b_bytes) {
+    const size_t want = std::max(b_bytes, ctx->q_onehot_cap * 2);  // geometric: see ensure_buf (api.cu)
     cudaStreamSynchronize(s);
     cudaFree(ctx->q_onehot);
     ctx->q_onehot = nullptr;
     ctx->q_onehot_cap = 0;
-    cudaError_t e = cudaMalloc((void **)&ctx->q_onehot, b_bytes);
+    cudaError_t e = cudaMalloc((void **)&ctx->q_onehot, want);
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(one-hot queries)", e);
-    ctx->q_onehot_cap = b_bytes;
+    ctx->q_onehot_cap = want;
   }
   int16_t *meta = reinterpret_cast<int16_t *>(ctx->q_onehot + (size_t)n_qtiles * MMA_N * KB);
   MmaParams P{};
