@@ -13,6 +13,7 @@ from smafa_b200 import api, synth
 D = int(os.environ.get("E2E_D", "1000000"))
 Q = int(os.environ.get("E2E_Q", "100000"))
 SUB = int(os.environ.get("E2E_SUB", "2000"))
+SUB_B = int(os.environ.get("E2E_SUB_B", "50"))   # Mode B: the reference sorts all D distances per query (~1 s each at 10 M)
 c_oracle.build()
 tmp = tempfile.mkdtemp(prefix="smafa_e2e_")
 db_sym = synth.make_db(D, L=60)
@@ -20,6 +21,7 @@ q_sym = synth.make_queries(db_sym, Q)
 synth.write_fasta(f"{tmp}/db.fna", synth.to_ascii(db_sym))
 synth.write_fasta(f"{tmp}/q.fna", synth.to_ascii(q_sym))
 synth.write_fasta(f"{tmp}/qsub.fna", synth.to_ascii(q_sym[:SUB]))
+synth.write_fasta(f"{tmp}/qsubb.fna", synth.to_ascii(q_sym[:SUB_B]))
 env = dict(os.environ, SMAFA_TIMING="1")
 
 
@@ -41,11 +43,12 @@ for args in (["--max-divergence", "5"], ["--max-divergence", "5", "--max-num-hit
     full = r.stdout
     print(f"smafa query {' '.join(args)}: {dt:.3f} s wall, {full.count(10)} lines, {Q * D / dt:.3e} comparisons/s end to end "
           f"(process start, CUDA init, file I/O included)\n{r.stderr.decode()}")
-    rs, dts = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/qsub.fna", *args])
-    ro, dto = run([c_oracle.CLI, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/qsub.fna", *args])
+    sub, subf = (SUB_B, "qsubb.fna") if "--max-num-hits" in args else (SUB, "qsub.fna")
+    rs, dts = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/{subf}", *args])
+    ro, dto = run([c_oracle.CLI, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/{subf}", *args])
     same = rs.stdout == ro.stdout
-    head = b"".join(l + b"\n" for l in full.split(b"\n") if l and int(l.split(b"\t", 1)[0]) < SUB)
-    print(f"  oracle CLI (1 thread) on the first {SUB} queries: {dto:.3f} s wall = {SUB * D / dto:.3e} comparisons/s; "
+    head = b"".join(l + b"\n" for l in full.split(b"\n") if l and int(l.split(b"\t", 1)[0]) < sub)
+    print(f"  oracle CLI (1 thread) on the first {sub} queries: {dto:.3f} s wall = {sub * D / dto:.3e} comparisons/s; "
           f"stdout identical to the GPU CLI: {same}; identical to the head of the full run: {head == ro.stdout}")
     if not same:
         sys.exit(2)

@@ -289,14 +289,34 @@ static inline void put_varint(std::vector<uint8_t> &o, uint64_t v) {
 }
 
 std::vector<uint8_t> serialize_db(const WindowDb &db) {
+  // windows are encoded on all host threads into per-chunk buffers and concatenated in order
+  const unsigned T = db.n >= 65536 ? host_threads() : 1;
+  std::vector<std::vector<uint8_t>> parts(T);
+  parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+    for (size_t t = t0; t < t1; ++t) {
+      const uint64_t lo = db.n * t / T, hi = db.n * (t + 1) / T;
+      std::vector<uint8_t> &o = parts[t];
+      o.reserve((hi - lo) * (1 + 9 * (size_t)db.W));
+      for (uint64_t i = lo; i < hi; ++i) {
+        put_varint(o, db.W);
+        for (uint32_t w = 0; w < db.W; ++w) put_varint(o, db.words[i * db.W + w]);
+      }
+    }
+  });
+  size_t body = 0;
+  for (const auto &v : parts) body += v.size();
   std::vector<uint8_t> o;
-  o.reserve(16 + db.n * (1 + 9 * (size_t)db.W));
+  o.reserve(32 + body);
   put_varint(o, DB_VERSION);
   put_varint(o, db.n);
-  for (uint64_t i = 0; i < db.n; ++i) {
-    put_varint(o, db.W);
-    for (uint32_t w = 0; w < db.W; ++w) put_varint(o, db.words[i * db.W + w]);
-  }
+  const size_t head = o.size();
+  o.resize(head + body);
+  std::vector<size_t> off(T + 1, head);
+  for (unsigned t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+  parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+    for (size_t t = t0; t < t1; ++t)
+      if (!parts[t].empty()) memcpy(o.data() + off[t], parts[t].data(), parts[t].size());
+  });
   if (db.L) { o.push_back(1); put_varint(o, db.L); }
   else o.push_back(0);
   return o;
