@@ -87,6 +87,8 @@ typedef struct smafa_stats {
   uint32_t kernel_used;    /* smafa_kernel actually run */
   float scan_ms;           /* device time of the scan kernels (CUDA events) */
   float total_ms;          /* device time of the whole call */
+  int32_t guess_bound;     /* bound of the optimistic first pass of the last batch (-1: none; csrc/guess.cu) */
+  uint32_t rescanned;      /* queries the first pass left unfinished (scanned again under the caller's bound) */
 } smafa_stats;
 
 int smafa_abi_version(void);

@@ -36,7 +36,7 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("candidates", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("retries", C.c_uint32), ("kernel_used", C.c_uint32), ("scan_ms", C.c_float),
-                ("total_ms", C.c_float)]
+                ("total_ms", C.c_float), ("guess_bound", C.c_int32), ("rescanned", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

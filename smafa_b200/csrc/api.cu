@@ -86,12 +86,14 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   ctx->kernel = kernel;
   ctx->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("SMAFA_NO_PREPASS")) ctx->disable_prepass = e[0] == '1';
+  if (const char *e = getenv("SMAFA_NO_GUESS")) ctx->disable_guess = e[0] == '1';
+  if (const char *e = getenv("SMAFA_FORCE_GUESS")) ctx->force_guess = atoi(e);
   if (const char *e = getenv("SMAFA_MMA_NSYM")) ctx->mma_nsym = (e[0] >= '2' && e[0] <= '5') ? (uint32_t)(e[0] - '0') : 3;
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
-  cudaHostAlloc((void **)&ctx->h_scalars, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
-  cudaMalloc((void **)&ctx->d_scalars, 4 * sizeof(unsigned long long));
+  cudaHostAlloc((void **)&ctx->h_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long), cudaHostAllocDefault);
+  cudaMalloc((void **)&ctx->d_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long));
   *out = ctx;
   return SMAFA_OK;
 }
@@ -112,6 +114,7 @@ extern "C" void smafa_ctx_destroy(smafa_ctx *ctx) {
   free_workspace(ctx);
   cudaFree(ctx->bound); cudaFree(ctx->hist); cudaFree(ctx->q_ref); cudaFree(ctx->q_planes);
   cudaFree(ctx->q_onehot);
+  cudaFree(ctx->per_query); cudaFree(ctx->unfinished); cudaFree(ctx->q_ref2);
   cudaFree(ctx->d_scalars);
   cudaFreeHost(ctx->h_scalars);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
@@ -358,6 +361,39 @@ static uint32_t pick_chunk(const smafa_ctx *ctx, uint64_t D, uint64_t n_qtiles, 
   return (uint32_t)((chunk + tile - 1) / tile * tile);
 }
 
+// Bound for the optimistic first pass (guess.cu): the largest distance g < bound0 at which the batch as a whole is
+// expected to emit no more than a budget of candidates, from the distance distribution of a strided sample of
+// (query, window) pairs.  Returns -1 when no such pass is worth running.
+static int guess_bound(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, const QueryPlan &plan,
+                       uint32_t need, cudaStream_t s, int *launches, int *rc_out) {
+  *rc_out = SMAFA_OK;
+  if (ctx->force_guess >= 0) return ctx->force_guess < plan.bound0 ? ctx->force_guess : -1;
+  const double pairs = (double)Qb * (double)db->D;
+  if (pairs < 2e9 || db->D < 65536 || Qb < 1024) return -1;  // small batches: the pre-pass alone is cheaper
+  const uint32_t q_stride = (Qb + 8191) / 8192;
+  const uint32_t n_d = (uint32_t)std::min<uint64_t>(2048, db->D);
+  const uint32_t d_stride = (uint32_t)(db->D / n_d);
+  unsigned long long *ghist = ctx->d_scalars + 8;
+  const int bins = guess_bins();
+  *launches += launch_sample_hist(q_ref_dev, Qb, q_stride, db->ref, d_stride, n_d, db->W, db->alphabet, ghist, s);
+  cudaError_t e = cudaMemcpyAsync(ctx->h_scalars + 8, ghist, bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { *rc_out = fail(ctx, SMAFA_E_CUDA, "sample histogram: %s", cudaGetErrorString(e)); return -1; }
+  const double n_q = (double)((Qb + q_stride - 1) / q_stride);
+  const double scale = pairs / (n_q * (double)n_d);  // real pairs per sampled pair
+  // Candidates cost ~1.5 ns of GPU time each against ~0.1 ns per comparison: 1e-5 of the pairs keeps them below
+  // ~15 % of the scan; the rows every query is owed anyway (need per query) come on top.
+  const double budget = 1e-5 * pairs + 2.0 * (double)need * (double)Qb;
+  double cum = 0;
+  int g = -1;
+  for (int t = 0; t < bins && t < plan.bound0; ++t) {
+    cum += (double)ctx->h_scalars[8 + t];
+    if (cum * scale > budget) break;
+    g = t;
+  }
+  return g;
+}
+
 // One batch (<= 2^20 queries, words already on the device).  Leaves *n_rows rows in ctx->hits.
 static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
                      const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st) {
@@ -365,18 +401,11 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   uint64_t want_cap = ctx->cand_cap_request ? ctx->cand_cap_request : DEFAULT_CAND_CAP;
   if ((rc = ensure_workspace(ctx, std::max<uint64_t>(want_cap, ctx->ws_cap)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, (size_t)Qb + 512))) return rc;  // padded: tile-wide vector loads
-  launch_init_bound(ctx->bound, Qb + 512, plan.bound0, s);
-  uint32_t hist_stride = (db->L + 1 + 3) / 4 * 4;  // rows 16-byte aligned for the vector scan in emit_candidate
-  if (plan.mode == MODE_KTH) {
-    if ((rc = ensure_buf(ctx, ctx->hist, ctx->hist_cap, (size_t)Qb * hist_stride))) return rc;
-    CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
-  }
+  const uint32_t hist_stride = (db->L + 1 + 3) / 4 * 4;  // rows 16-byte aligned for the vector scan in emit_candidate
+  if (plan.mode == MODE_KTH && (rc = ensure_buf(ctx, ctx->hist, ctx->hist_cap, (size_t)Qb * hist_stride))) return rc;
   unsigned long long *cand_count = ctx->d_scalars + 0;
-  CU(cudaMemsetAsync(cand_count, 0, sizeof(unsigned long long), s));
 
   ScanParams p{};
-  p.q_ref = q_ref_dev;
-  p.Q = Qb;
   p.d_planes = db->planes;
   p.d_ref = db->ref;
   p.D = (uint32_t)db->D;
@@ -400,41 +429,93 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   if (kernel == SMAFA_KERNEL_MMA && !mma_supported(db)) kernel = SMAFA_KERNEL_POPC;
   // a fixed bound that admits everything would send every accumulator down the MMA slow path
   if (kernel == SMAFA_KERNEL_MMA && plan.mode == MODE_FIXED && plan.bound0 >= (int)db->L) kernel = SMAFA_KERNEL_POPC;
-  ctx->mma_bound0 = plan.bound0;
 
+  int *q_invalid = ctx->d_scratch_flag();
+  int launches = 0;
+  // One scan of `nq` queries (words at q_dev) under the starting bound b0; candidates are appended at *cand_count.
+  auto scan_pass = [&](const uint64_t *q_dev, uint32_t nq, int b0, bool prepass, int kern) -> int {
+    int r;
+    launch_init_bound(ctx->bound, nq + 512, b0, s);
+    if (plan.mode == MODE_KTH) CU(cudaMemsetAsync(ctx->hist, 0, (size_t)nq * hist_stride * sizeof(uint32_t), s));
+    launches += 1;
+    p.q_ref = q_dev;
+    p.Q = nq;
+    if (kern == -1) {
+      launches += launch_scan_generic(p, pick_chunk(ctx, db->D, (nq + 127) / 128, 256), s);
+      return SMAFA_OK;
+    }
+    if (kern == SMAFA_KERNEL_MMA && nq < 64) kern = SMAFA_KERNEL_POPC;
+    if ((r = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)nq + 256) * db->row_words))) return r;
+    launch_pack_planes(q_dev, nq, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
+    launches += 1;
+    p.q_planes = ctx->q_planes;
+    // No useful starting bound (no or a loose --max-divergence): estimate one on a strided db
+    // sample first, otherwise the first tiles of the scan would emit nearly every pair.
+    if (prepass) {
+      const uint32_t n_tiles = (uint32_t)((db->D + 255) / 256);
+      if (n_tiles >= 32) {
+        uint32_t sample_tiles = std::min<uint32_t>(std::max<uint32_t>(n_tiles / 32, 16), 224);
+        launches += launch_bound_prepass(p, std::max<uint32_t>(1, n_tiles / sample_tiles), s);
+      }
+    }
+    if (kern == SMAFA_KERNEL_MMA) {
+      ctx->mma_bound0 = b0;
+      int l = mma_scan(ctx, db, p, s, ctx->mma_dump);
+      if (l < 0) return l;
+      launches += l;
+    } else {
+      const bool early = b0 * 4 <= (int)db->L;
+      uint32_t r4 = nq >= 148u * 256u * 2u ? 4 : 1;
+      launches += launch_scan_popc(p, early, pick_chunk(ctx, db->D, (nq + 256 * r4 - 1) / (256 * r4), popc_tile_rows()), s);
+    }
+    return SMAFA_OK;
+  };
+
+  const bool loose = plan.mode != MODE_FIXED && plan.bound0 * 3 > (int)db->L && !ctx->disable_prepass;
+  const uint32_t need = plan.mode == MODE_KTH ? plan.k_scan : 1;  // rows that finish a query under a guessed bound
   uint64_t n_cand = 0;
   for (;;) {
-    int *q_invalid = ctx->d_scratch_flag();
     CU(cudaMemsetAsync(q_invalid, 0, sizeof(int), s));
+    CU(cudaMemsetAsync(cand_count, 0, sizeof(unsigned long long), s));
+    launches = 2;
     cudaEventRecord(ctx->ev[0], s);
-    int launches = 2;
-    if (kernel == -1) {
-      uint32_t chunk = pick_chunk(ctx, db->D, (Qb + 127) / 128, 256);
-      launches += launch_scan_generic(p, chunk, s);
+    int g = -1;
+    if (kernel != -1 && loose && !ctx->disable_guess && db->L <= 64) {
+      g = guess_bound(ctx, db, q_ref_dev, Qb, plan, need, s, &launches, &rc);
+      if (rc) return rc;
+    }
+    if (g >= 0) {
+      // ---- first pass under the guessed bound; second pass for the queries it did not finish (guess.cu) ----
+      if ((rc = scan_pass(q_ref_dev, Qb, g, false, kernel))) return rc;
+      CU(cudaMemcpyAsync(ctx->h_scalars + 0, cand_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      const uint64_t n1 = ctx->h_scalars[0];
+      if (n1 > ctx->ws_cap) { n_cand = n1; break; }  // overflow: the caller retries with a smaller batch
+      if ((rc = ensure_buf(ctx, ctx->per_query, ctx->per_query_cap, (size_t)Qb))) return rc;
+      if ((rc = ensure_buf(ctx, ctx->unfinished, ctx->unfinished_cap, (size_t)Qb))) return rc;
+      uint32_t *n_list = reinterpret_cast<uint32_t *>(ctx->d_scalars + 4);
+      launch_count_per_query(ctx->cand, n1, Qb, ctx->per_query, s);
+      launch_list_unfinished(ctx->per_query, Qb, need, ctx->unfinished, n_list, s);
+      launches += 2;
+      CU(cudaMemcpyAsync(ctx->h_scalars + 4, n_list, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      const uint32_t n_open = *reinterpret_cast<uint32_t *>(ctx->h_scalars + 4);
+      if (st) st->rescanned += n_open;
+      if (n_open) {
+        if ((rc = ensure_buf(ctx, ctx->q_ref2, ctx->q_ref2_cap, (size_t)n_open * db->W))) return rc;
+        launch_gather_queries(q_ref_dev, ctx->unfinished, n_open, db->W, ctx->q_ref2, s);
+        // the unfinished queries' first-pass candidates would come again in the second pass: drop them
+        unsigned long long *n_keep = ctx->d_scalars + 3;
+        launch_keep_finished(ctx->cand, n1, ctx->per_query, need, ctx->fw.keys_sorted, n_keep, s);
+        CU(cudaMemcpyAsync(ctx->cand, ctx->fw.keys_sorted, n1 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(cand_count, n_keep, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        launches += 3;
+        if ((rc = scan_pass(ctx->q_ref2, n_open, plan.bound0, true, kernel))) return rc;
+        launch_remap_queries(ctx->cand, n_keep, cand_count, ctx->ws_cap, ctx->unfinished, s);
+        launches += 1;
+      }
     } else {
-      if ((rc = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)Qb + 256) * db->row_words))) return rc;
-      launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
-      launches += 1;
-      p.q_planes = ctx->q_planes;
-      // No useful starting bound (no or a loose --max-divergence): estimate one on a strided db
-      // sample first, otherwise the first tiles of the scan would emit nearly every pair.
-      if (plan.mode != MODE_FIXED && plan.bound0 * 3 > (int)db->L && !ctx->disable_prepass) {
-        const uint32_t n_tiles = (uint32_t)((db->D + 255) / 256);
-        if (n_tiles >= 32) {
-          uint32_t sample_tiles = std::min<uint32_t>(std::max<uint32_t>(n_tiles / 32, 16), 224);
-          launches += launch_bound_prepass(p, std::max<uint32_t>(1, n_tiles / sample_tiles), s);
-        }
-      }
-      if (kernel == SMAFA_KERNEL_MMA) {
-        int l = mma_scan(ctx, db, p, s, ctx->mma_dump);
-        if (l < 0) return l;
-        launches += l;
-      } else {
-        const bool early = plan.bound0 * 4 <= (int)db->L;
-        uint32_t r = Qb >= 148u * 256u * 2u ? 4 : 1;
-        uint32_t chunk = pick_chunk(ctx, db->D, (Qb + 256 * r - 1) / (256 * r), popc_tile_rows());
-        launches += launch_scan_popc(p, early, chunk, s);
-      }
+      if ((rc = scan_pass(q_ref_dev, Qb, plan.bound0, loose, kernel))) return rc;
     }
     cudaEventRecord(ctx->ev[1], s);
     CU(cudaMemcpyAsync(ctx->h_scalars + 0, cand_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -448,14 +529,12 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       st->scan_ms += ms;
       st->kernel_used = kernel == -1 ? 0 : (uint32_t)kernel;
       st->kernel_launches += launches;
+      st->guess_bound = g;
     }
     if (kernel != -1 && (int)(ctx->h_scalars[2] & 0xffffffffu) != 0) {
       // a query holds words that are not valid one-hot codes: redo the batch on the reference
       // word layout, which reproduces popcount(a^b)/2 for arbitrary words
       kernel = -1;
-      launch_init_bound(ctx->bound, Qb, plan.bound0, s);
-      if (plan.mode == MODE_KTH) CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
-      CU(cudaMemsetAsync(cand_count, 0, sizeof(unsigned long long), s));
       continue;
     }
     break;

@@ -112,16 +112,18 @@ __device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, i
         uint4 c[16];
 #pragma unroll
         for (int v = 0; v < 16; ++v) c[v] = v < nvec ? __ldcg(hv + v) : make_uint4(0, 0, 0, 0);
+        bool open = true;  // the crossing bin has not been reached yet
 #pragma unroll
         for (int v = 0; v < 16; ++v) {
-          const uint32_t cc[4] = {c[v].x, c[v].y, c[v].z, c[v].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int t = v * 4 + j;
-            if (t < bound) {
-              cum += cc[j];
-              if (cum >= p.k && t < nb) nb = t;
+          if (open && v < nvec) {
+            const uint32_t s0 = cum + c[v].x, s1 = s0 + c[v].y, s2 = s1 + c[v].z, s3 = s2 + c[v].w;
+            if (s3 >= p.k) {
+              // bins >= bound of the last vector may hold stale emissions: a crossing there tightens nothing
+              const int t = v * 4 + (s0 >= p.k ? 0 : (s1 >= p.k ? 1 : (s2 >= p.k ? 2 : 3)));
+              if (t < bound) nb = t;
+              open = false;
             }
+            cum = s3;
           }
         }
       } else {  // long windows (generic kernel only)

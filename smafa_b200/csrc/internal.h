@@ -19,6 +19,8 @@ struct smafa_ctx {
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   int alphabet = 0;               // Alphabet of the dbs uploaded next and of smafa_cluster input (smafa_ctx_set_alphabet)
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
+  bool disable_guess = false;     // SMAFA_NO_GUESS=1: no optimistic first pass under a guessed bound (guess.cu)
+  int force_guess = -1;           // SMAFA_FORCE_GUESS=g: use g as the guessed bound whatever the sample says (tests)
   int32_t *mma_dump = nullptr;    // debug hook (smafa_debug_mma_dump)
   int mma_bound0 = 0;             // initial bound of the batch being scanned (bias of the query operand)
   cudaStream_t stream = nullptr;
@@ -36,7 +38,13 @@ struct smafa_ctx {
   uint64_t *q_ref = nullptr;      size_t q_ref_cap = 0;
   uint32_t *q_planes = nullptr;   size_t q_planes_cap = 0;
   uint8_t *q_onehot = nullptr;    size_t q_onehot_cap = 0;
-  // scalars: [0] candidate count, [1] selected count, [2] scratch flag, [3] spare
+  // optimistic first pass (guess.cu)
+  uint32_t *per_query = nullptr;  size_t per_query_cap = 0;   // candidates per query after the first pass
+  uint32_t *unfinished = nullptr; size_t unfinished_cap = 0;  // query numbers that need the second pass
+  uint64_t *q_ref2 = nullptr;     size_t q_ref2_cap = 0;      // their words, compacted
+  // scalars: [0] candidate count, [1] selected count, [2] scratch flag, [3] candidates kept after the first
+  // pass, [4] unfinished queries, [8..8+guess_bins) sampled distance histogram
+  static constexpr int N_SCALARS = 8 + 72;
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;  // pinned mirror
   int *d_scratch_flag() { return reinterpret_cast<int *>(d_scalars + 2); }

@@ -23,6 +23,18 @@ void launch_distances(const uint64_t *q_ref, uint32_t Q, const uint64_t *d_ref, 
                       uint16_t *out, cudaStream_t s);
 int popc_tile_rows();
 
+// guess.cu -- optimistic first pass under a guessed bound (see the file header)
+int launch_sample_hist(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t d_stride,
+                       uint32_t n_d, uint32_t W, int alphabet, unsigned long long *ghist, cudaStream_t s);
+int guess_bins();
+void launch_count_per_query(const uint64_t *cand, uint64_t n, uint32_t Q, uint32_t *per_query, cudaStream_t s);
+void launch_list_unfinished(const uint32_t *per_query, uint32_t Q, uint32_t need, uint32_t *list, uint32_t *n_list, cudaStream_t s);
+void launch_gather_queries(const uint64_t *q_ref, const uint32_t *list, uint32_t n, uint32_t W, uint64_t *out, cudaStream_t s);
+void launch_keep_finished(const uint64_t *cand, uint64_t n, const uint32_t *per_query, uint32_t need, uint64_t *out,
+                          unsigned long long *n_out, cudaStream_t s);
+void launch_remap_queries(uint64_t *cand, const unsigned long long *begin, const unsigned long long *end, uint64_t cap,
+                          const uint32_t *list, cudaStream_t s);
+
 // finalize.cu
 struct FinalizeWorkspace {
   uint64_t *keys_sorted = nullptr;  // [cap]

@@ -20,10 +20,12 @@
 // the global bounds every tile by the otherwise idle producer warp (stale = looser = still a
 // superset).
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
+// Warp roles (448 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
 //   warp 0 : bulk-copy producer (B once per item, A tiles through a 3-stage mbarrier ring) + bias refresh
 //   warp 1 : TMEM allocation, single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-9 : epilogue, two warps per TMEM lane quarter (128 columns each, tcgen05.ld 32x32b.x32)
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter (128 columns each, tcgen05.ld 32x32b.x32); survivors of the
+//               sign filter go to a per-warp shared-memory ring
+//   warps 10-13 : verifiers, drain the rings (exact distance, candidate emission, bound tightening)
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -37,7 +39,10 @@ constexpr int MMA_M = 128;      // db windows per tile
 constexpr int MMA_N = 256;      // queries per tile
 // Epilogue warps: EPI_WARPS/4 per TMEM lane quarter (a warp may only read the 32 lanes of quarter warp%4),
 // each draining MMA_N / (EPI_WARPS/4) accumulator columns of every tile.
-constexpr int mma_threads(int epi_warps) { return 64 + 32 * epi_warps; }
+// Verifier warps: consume the survivor rings the epilogue warps fill (exact re-check + emission), so that the
+// latency of verification never sits between two accumulator drains.
+constexpr int MMA_VER_WARPS = 4;
+constexpr int mma_threads(int epi_warps) { return 64 + 32 * epi_warps + 32 * MMA_VER_WARPS; }
 
 struct MmaParams {
   ScanParams sp;
@@ -189,12 +194,18 @@ __host__ __device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t 
   return (row >> 3) * (8 * KB) + (kbyte >> 4) * 128 + (row & 7) * 16 + (kbyte & 15);
 }
 
-// Survivors of the sign filter are not verified on the spot (that would serialise up to 32 divergent
-// lanes and stall the TMEM drain): each epilogue warp appends them to a private shared-memory list and
-// drains the list cooperatively -- one survivor per lane, all exact distances in flight together, one
-// global atomicAdd per warp-full of accepted candidates.  Everything here is inlined: a call inside the
-// epilogue loop makes ptxas keep loop state in local memory (seen in the v5 SASS).
-constexpr int MMA_LIST_CAP = 256;  // survivors per epilogue warp between drains
+// Survivors of the sign filter are not verified by the warp that finds them: verification is a chain of
+// dependent L2 round trips (reference words, bound, candidate slot, histogram), and with only two accumulator
+// buffers one epilogue warp stuck in it stalls the MMA pipeline of the whole CTA within a tile (ncu on the
+// unbounded top-k scan: epilogue warps 45 % of their samples on TFULL, tensor pipe 48 % active).  Each epilogue
+// warp instead appends (query, window) pairs to a private shared-memory ring; MMA_VER_WARPS verifier warps
+// drain the rings -- one survivor per lane, all exact distances in flight together, one global atomicAdd per
+// warp-full of accepted candidates.  Everything here is inlined: a call inside the epilogue loop makes ptxas
+// keep loop state in local memory (seen in the v5 SASS).
+constexpr int MMA_LIST_CAP = 256;  // ring entries per epilogue warp (power of two)
+
+__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_shared_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
 __device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uint32_t j, int &d, int &bnd) {
   if (q >= sp.Q || j >= sp.d_end) return false;
@@ -221,31 +232,28 @@ __device__ __forceinline__ void mma_verify_emit_warp(const ScanParams &sp, bool 
   }
 }
 
-__device__ __forceinline__ void mma_drain_list(const ScanParams &sp, const uint2 *list, uint32_t n, uint32_t lane) {
-#pragma unroll 1
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    uint2 e = make_uint2(0, 0);
-    if (i < n) e = list[i];
-    mma_verify_emit_warp(sp, i < n, e.x, e.y, lane);
-  }
-  __syncwarp();
-}
-
 __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;  // opaque to the optimiser: keeps the reduction a tree instead of one dependent LOP3 chain
   asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-// AND of 32 registers, depth 4
-__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
-  uint32_t t[11];
+// AND of 32 registers, depth 4.  The intermediate levels are kept: the slow path descends through them to the
+// registers that hold a survivor instead of testing all 64 sign bits.
+struct AndTree {
+  uint32_t t[11];  // t[g] = AND of registers 3g..3g+2 (t[10]: registers 30, 31)
+  uint32_t u[4];   // u[h] = AND of t[3h..3h+2] (u[3]: t[9], t[10])
+  uint32_t all;
+};
+__device__ __forceinline__ AndTree and_tree32(const uint32_t (&v)[32]) {
+  AndTree a;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) t[i] = and3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-  t[10] = v[30] & v[31];
-  const uint32_t u0 = and3(t[0], t[1], t[2]), u1 = and3(t[3], t[4], t[5]), u2 = and3(t[6], t[7], t[8]);
-  const uint32_t u3 = t[9] & t[10];
-  return and3(u0, u1, u2) & u3;
+  for (int i = 0; i < 10; ++i) a.t[i] = and3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  a.t[10] = v[30] & v[31];
+#pragma unroll
+  for (int h = 0; h < 3; ++h) a.u[h] = and3(a.t[3 * h], a.t[3 * h + 1], a.t[3 * h + 2]);
+  a.u[3] = a.t[9] & a.t[10];
+  a.all = and3(a.u[0], a.u[1], a.u[2]) & a.u[3];
+  return a;
 }
 
 // NSYM = 5: operands hold all five symbols, D = matches - need exactly.
@@ -267,7 +275,10 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
   uint8_t *sA = smem + B_BUFS * B_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + B_BUFS * B_BYTES + STAGES * A_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
-  uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(bars) + 256);  // [MMA_EPI_WARPS][MMA_LIST_CAP]
+  uint32_t *ring_ctl = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bars) + 256);  // tail[16] head[16] done[16]
+  uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(bars) + 512);  // [MMA_EPI_WARPS][MMA_LIST_CAP]
+  uint32_t *ring_tail = ring_ctl, *ring_head = ring_ctl + 16, *ring_done = ring_ctl + 32;
+  static_assert(EPI_WARPS <= 16 && EPI_WARPS % MMA_VER_WARPS == 0, "ring control block");
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
   auto B_EMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 6 + b); };
   auto B_READY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 8 + b); };
 
+  if (threadIdx.x < 48) ring_ctl[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
@@ -421,40 +433,58 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
-    // ===== epilogue: TMEM -> registers, sign-AND filter, exact re-check of survivors =====
+  } else if (warp < 2 + MMA_EPI_WARPS) {
+    // ===== epilogue: TMEM -> registers, sign-AND filter, survivors -> ring =====
     const uint32_t quarter = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const uint32_t part = (warp - 2) >> 2;      // which column range of the tile this warp drains
     constexpr uint32_t COLS_PER_WARP = MMA_N / (MMA_EPI_WARPS / 4);
     constexpr uint32_t COLS_PER_LD = PACK16 ? 64 : 32;
     constexpr uint32_t CHUNKS = COLS_PER_WARP / COLS_PER_LD;
     uint2 *my_list = lists + (warp - 2) * MMA_LIST_CAP;
-    uint32_t count = 0;  // entries in my_list (warp-uniform)
+    uint32_t tail = 0, head_seen = 0;  // ring positions (free-running, warp-uniform); head_seen = last head read
     uint32_t tcount = 0;
     // Slow path, entered by the whole warp when any lane saw a non-negative accumulator in chunk c:
-    // per-lane survivor bit masks, a warp scan for the list offsets, then a short per-lane store loop.
-    auto slow = [&](const uint32_t (&v)[32], uint32_t qc, uint32_t row) {
+    // per-lane survivor bit masks, a warp scan for the ring offsets, then a short per-lane store loop.
+    auto slow = [&](const uint32_t (&v)[32], const AndTree &tr, uint32_t hitmask, uint32_t qc, uint32_t row) {
+      constexpr uint32_t SIGNS = PACK16 ? 0x80008000u : 0x80000000u;
       uint32_t m0 = 0, m1 = 0;  // bit i: accumulator i (pack16: low / high half of register i) is >= 0
+      // Survivors are sparse whenever this path matters, so the 64 sign bits are not all tested: only the lanes
+      // that hold one descend the AND tree (9-register blocks, then 3-register groups) to the registers involved.
+      if ((tr.all & SIGNS) != SIGNS) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if constexpr (PACK16) {
-          m0 |= ((~v[i] >> 15) & 1u) << i;
-          m1 |= (~v[i] >> 31) << i;
-        } else {
-          m0 |= (~v[i] >> 31) << i;
+        for (int h = 0; h < 4; ++h) {
+          if ((tr.u[h] & SIGNS) != SIGNS) {
+#pragma unroll
+            for (int g = 3 * h; g < 3 * h + 3 && g < 11; ++g) {
+              if ((tr.t[g] & SIGNS) != SIGNS) {
+#pragma unroll
+                for (int i = 3 * g; i < 3 * g + 3 && i < 32; ++i) {
+                  if constexpr (PACK16) {
+                    m0 |= ((~v[i] >> 15) & 1u) << i;
+                    m1 |= (~v[i] >> 31) << i;
+                  } else {
+                    m0 |= (~v[i] >> 31) << i;
+                  }
+                }
+              }
+            }
+          }
         }
       }
+      __syncwarp();
       const uint32_t n = __popc(m0) + __popc(m1);
-      uint32_t incl = n;
+      uint32_t incl, total;
+      if ((hitmask & (hitmask - 1)) == 0) {  // one lane holds all the survivors (the common case): no scan
+        total = __shfl_sync(0xffffffffu, n, __ffs(hitmask) - 1);
+        incl = n;  // the holder's exclusive offset is incl - n = 0; the other lanes store nothing
+      } else {
+        incl = n;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += y;
-      }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      if (count + total > (uint32_t)MMA_LIST_CAP) {
-        mma_drain_list(sp, my_list, count, lane);
-        count = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+          if ((int)lane >= d) incl += y;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
       }
       if (total > (uint32_t)MMA_LIST_CAP) {
         // a flood (bound admits > 1/4 of the chunk): verify straight from the masks, warp-wide per bit
@@ -464,20 +494,33 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
           if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row, lane);
         }
       } else {
-        uint32_t off = count + incl - n;
+        if (tail + total - head_seen > (uint32_t)MMA_LIST_CAP) {  // ring full: wait for the verifier warp
+          const long long t0 = clock64();
+          do {
+            head_seen = ld_shared_volatile(ring_head + (warp - 2));
+            if (clock64() - t0 > 8000000000ll) __trap();
+          } while (tail + total - head_seen > (uint32_t)MMA_LIST_CAP);
+          __threadfence_block();  // the slots were read before the head moved
+        }
+        uint32_t off = tail + incl - n;
         while (m0) {
           const int i = __ffs(m0) - 1;
           m0 &= m0 - 1;
-          my_list[off++] = make_uint2(qc + (PACK16 ? 2 * i : i), row);
+          my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row);
         }
         if constexpr (PACK16) {
           while (m1) {
             const int i = __ffs(m1) - 1;
             m1 &= m1 - 1;
-            my_list[off++] = make_uint2(qc + 2 * i + 1, row);
+            my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row);
           }
         }
-        count += total;
+        tail += total;
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();  // entries before the new tail
+          st_shared_volatile(ring_tail + (warp - 2), tail);
+        }
       }
       __syncwarp();
     };
@@ -496,9 +539,10 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
           else tc_ld32(taddr + c * 32, v);
         };
         auto process = [&](const uint32_t (&v)[32], uint32_t c) {
-          const uint32_t acc = and_tree32(v);
-          const bool hit = PACK16 ? (acc & 0x80008000u) != 0x80008000u : (int)acc >= 0;
-          if (__any_sync(0xffffffffu, hit)) slow(v, qbase + c * COLS_PER_LD, row);
+          const AndTree tr = and_tree32(v);
+          const bool hit = PACK16 ? (tr.all & 0x80008000u) != 0x80008000u : (int)tr.all >= 0;
+          const uint32_t hitmask = __ballot_sync(0xffffffffu, hit);
+          if (hitmask) slow(v, tr, hitmask, qbase + c * COLS_PER_LD, row);
         };
         uint32_t va[32];
         if (P.dump != nullptr && item == 0 && t == t_begin) {  // debug hook, off the hot path
@@ -545,16 +589,72 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
             if (c + 2 < CHUNKS) tc_wait_ld();
           }
         }
-        // Lazy drain: verification is latency-bound (dependent L2 round trips), so survivors are
-        // batched until half the list is full -- 4+ full warp iterations per drain -- and the rest is
-        // flushed once the warp has no tiles left.
-        if (count >= (uint32_t)MMA_LIST_CAP / 2) {
-          mma_drain_list(sp, my_list, count, lane);
-          count = 0;
-        }
       }
     }
-    if (count) mma_drain_list(sp, my_list, count, lane);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      st_shared_volatile(ring_done + (warp - 2), 1u);
+    }
+  } else {
+    // ===== verifier: exact re-check + emission of the survivors the epilogue warps queued =====
+    constexpr uint32_t RPV = MMA_EPI_WARPS / MMA_VER_WARPS;  // rings per verifier warp
+    const uint32_t first = (warp - 2 - MMA_EPI_WARPS) * RPV;
+    uint32_t head[RPV], tl[RPV];
+#pragma unroll
+    for (uint32_t r = 0; r < RPV; ++r) head[r] = 0;
+    uint32_t waited = 0, nap = 128;
+    for (;;) {
+      // Verification is a chain of dependent L2 round trips whose cost does not depend on how many lanes take
+      // part, so a batch is gathered across this warp's rings and started only when it is full -- or when the
+      // survivors have waited for a while, or their producers are done.
+      bool all_done = true;
+      uint32_t total = 0;
+#pragma unroll
+      for (uint32_t r = 0; r < RPV; ++r) {
+        // `done` is read before the tail: a ring seen done has its final tail published
+        const uint32_t done = ld_shared_volatile(ring_done + first + r);
+        __threadfence_block();
+        tl[r] = ld_shared_volatile(ring_tail + first + r);
+        total += tl[r] - head[r];
+        if (!done) all_done = false;
+      }
+      if (total == 0) {
+        if (all_done) break;
+        // Idle is the normal state (tight bounds: a few survivors per thousand tiles), so the poll backs off to
+        // ~4 us: frequent polling cost the tile loop 3 % (the verifiers share issue slots with the epilogue warps).
+        // A hang is impossible here: the epilogue warps' own waits are bounded.
+        waited = 0;
+        nap = min(nap * 2u, 4096u);
+        __nanosleep(nap);
+        continue;
+      }
+      if (total < 32u && !all_done && waited < 16u) {  // give a partial batch ~10 us to fill up
+        ++waited;
+        __nanosleep(512);
+        continue;
+      }
+      waited = 0;
+      nap = 128;
+      __threadfence_block();  // entries are read after the tails
+      uint2 e = make_uint2(0, 0);
+      uint32_t taken = 0;
+#pragma unroll
+      for (uint32_t r = 0; r < RPV; ++r) {
+        const uint32_t n = min(tl[r] - head[r], 32u - taken);
+        if (lane >= taken && lane < taken + n) e = lists[(first + r) * MMA_LIST_CAP + ((head[r] + lane - taken) & (MMA_LIST_CAP - 1))];
+        head[r] += n;
+        taken += n;
+      }
+      __syncwarp();
+      if (lane < RPV) {
+        __threadfence_block();  // the slots are in registers: the producers may reuse them
+#pragma unroll
+        for (uint32_t r = 0; r < RPV; ++r)
+          if (lane == r) st_shared_volatile(ring_head + first + r, head[r]);
+      }
+      mma_verify_emit_warp(sp, lane < taken, e.x, e.y, lane);
+    }
   }
 
   tc_fence_before();
@@ -777,7 +877,7 @@ void mma_db_free(smafa_db *db) {
 
 template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2>
 static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
-  constexpr size_t smem = (size_t)B_BUFS * MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 256 +
+  constexpr size_t smem = (size_t)B_BUFS * MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 512 +
                           (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
   static_assert(smem <= 232448, "more than 227 KB of shared memory");
   auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS>;
@@ -831,9 +931,9 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, n_items);
   cudaError_t e;
   const bool wide = mma_pb(db->mma_nsym, db->L) == 64;
-  // Epilogue shape: 8 warps + .pack::16b TMEM loads measured best (profiles/r01_epilogue_variants.txt);
-  // SMAFA_MMA_EPI=16 / SMAFA_MMA_PACK16=0 keep the other shapes of the default encoding reachable.
-  static const int epi = getenv("SMAFA_MMA_EPI") ? atoi(getenv("SMAFA_MMA_EPI")) : 8;
+  // Epilogue shape: 8 warps + .pack::16b TMEM loads measured best (profiles/r01_epilogue_variants.txt; the 16-warp
+  // shape measured there is gone since the verifier warps took its register budget); SMAFA_MMA_PACK16=0 keeps the
+  // unpacked loads of the default encoding reachable.
   static const bool pack16 = getenv("SMAFA_MMA_PACK16") ? atoi(getenv("SMAFA_MMA_PACK16")) != 0 : true;
   switch (db->mma_nsym) {
     case MMA_ENC_AA: e = launch_mma<13, (int)MMA_ENC_AA, 2, 8, true, 1>(P, grid, s); break;
@@ -842,7 +942,6 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
     case 2: e = wide ? launch_mma<4, 2, 4, 8, true>(P, grid, s) : launch_mma<2, 2, 4, 8, true>(P, grid, s); break;
     default:
       if (!wide) e = launch_mma<3, 3, 4, 8, true>(P, grid, s);
-      else if (epi == 16) e = pack16 ? launch_mma<6, 3, 4, 16, true>(P, grid, s) : launch_mma<6, 3, 4, 16, false>(P, grid, s);
       else e = pack16 ? launch_mma<6, 3, 4, 8, true>(P, grid, s) : launch_mma<6, 3, 4, 8, false>(P, grid, s);
       break;
   }

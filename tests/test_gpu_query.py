@@ -284,6 +284,74 @@ def test_cluster_matches_oracle(ctx, L, t, n, kernel):
     assert (cof.astype(np.int64) == remap[want_cof[keep]]).all()
 
 
+# ---- optimistic first pass under a guessed bound (csrc/guess.cu) -----------------------------------
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("guess", [0, 2, 7, 25])
+def test_guessed_bound_pass_is_exact(guess, kernel, monkeypatch):
+    """Unbounded selection scans the batch under a guessed bound first and re-scans only the queries that did not find
+    their k windows within it.  SMAFA_FORCE_GUESS pins the guess (the sampled estimate only switches on for >= 2e9
+    comparisons), so every split between the two passes is exercised: nothing finished (0), some, all (25)."""
+    monkeypatch.setenv("SMAFA_FORCE_GUESS", str(guess))
+    c = smafa_b200.Context(0, kernel)
+    try:
+        for L in (20, 60):
+            db_sym = synth.make_db(6000, L=L, seed=700 + L, family=8, max_subs=min(5, L), noise=0.03)
+            q_sym = synth.make_queries(db_sym, 700, seed=800 + L, max_subs=min(8, L), noise=0.03)
+            # a third of the queries are unrelated to the db: they never finish under a small guess
+            q_sym[::3] = synth.random_symbols(len(q_sym[::3]), L, seed=900 + L)
+            db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+            d = c.upload(db, L)
+            rescanned = []
+            for m, k, r in [(None, None, None), (None, 1, None), (None, 2, None), (None, 10, None), (None, 10, 1),
+                            (L - 1, 25, None), (None, 5999, None), (None, 7000, None), (3, 10, None)]:
+                got, st = c.query(d, q, L, max_divergence=m, max_num_hits=k, limit_per_sequence=r, return_stats=True)
+                want = c_oracle.query(db, L, q, L, m, k, r)
+                assert got.shape == want.shape and (got == want).all(), (L, m, k, r, guess)
+                rescanned.append((st["guess_bound"], st["rescanned"]))
+            d.close()
+            # the pass ran for the loose modes (not for k > D, which keeps everything, nor for --max-divergence 3)
+            want_g = guess if guess < L else -1  # a guess that is not below the caller's bound is pointless
+            assert rescanned[0][0] == want_g and rescanned[3][0] == want_g
+            assert rescanned[7][0] == -1 and rescanned[8][0] == -1
+            if guess == 0:
+                assert rescanned[3][1] > 0
+    finally:
+        c.close()
+
+
+def test_guessed_bound_from_the_sample(ctx):
+    """Large enough for the sampled estimate (no forcing): unbounded top-10 and best-hit on 20 k x 200 k, oracle on a
+    query subsample, and the same rows with the pass switched off."""
+    L, D, Q = 60, 200_000, 20_000
+    db_sym = synth.make_db(D, L=L, seed=11)
+    q_sym = synth.make_queries(db_sym, Q, seed=12)
+    q_sym[::7] = synth.random_symbols(len(q_sym[::7]), L, seed=13)  # queries without relatives in the db
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    ctx.set_kernel("auto")
+    d = ctx.upload(db, L)
+    for k in (None, 10):
+        got, st = ctx.query(d, q, L, max_num_hits=k, return_stats=True)
+        assert 0 <= st["guess_bound"] < L and st["rescanned"] >= Q // 8
+        want = c_oracle.query(db, L, q[:140], L, None, k, None, threads=os.cpu_count() or 1)
+        sub = got[got[:, 0] < 140]
+        assert sub.shape == want.shape and (sub == want).all()
+        x = np.bitwise_count(db[got[:, 1]] ^ q[got[:, 0]]).sum(axis=1) // 2
+        assert (x == got[:, 2]).all()
+        os.environ["SMAFA_NO_GUESS"] = "1"
+        try:
+            c2 = smafa_b200.Context(0, "auto")
+            d2 = c2.upload(db, L)
+            plain, st2 = c2.query(d2, q, L, max_num_hits=k, return_stats=True)
+            d2.close()
+            c2.close()
+        finally:
+            del os.environ["SMAFA_NO_GUESS"]
+        assert st2["guess_bound"] == -1
+        assert plain.shape == got.shape and (plain == got).all()
+    d.close()
+
+
 # ---- full-size checks (BASELINE config 2 shape): oracle on a query subsample + properties -------
 
 @pytest.mark.parametrize("kernel", KERNELS)
