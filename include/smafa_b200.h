@@ -148,7 +148,8 @@ int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc_de
 
 /* Multi-GPU merge: applies the reference's selection to the union of the
  * per-shard candidate lists (after the NCCL all-gather).  In-place on a device buffer of n
- * rows; *n_out rows remain, sorted in print order. */
+ * rows; *n_out rows remain, sorted in print order.  *n_out is final on return; the rows themselves are
+ * stream-ordered (valid for work queued on `stream` after the call, or after synchronising it). */
 int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n, int64_t max_divergence,
                     int64_t max_num_hits, uint64_t *n_out, void *stream);
 

@@ -1,0 +1,104 @@
+"""BASELINE configs[2] at full size under torchrun (one rank per GPU): 1 M queries x 10 M 60-nt windows, the db
+row-sharded over the ranks, per-shard candidates merged with the NCCL all-gather.  Prints ONE JSON line from rank 0
+with comparisons/s (CUDA events, max over ranks), the scan kernel's share, and the parity verdict: the rows of a
+query subsample spread over the batch must equal the oracle's on the WHOLE db bit for bit, and every row must pass
+the size-independent properties (print order, one distance per query in Mode A, distances re-derived).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/config3_multi.py
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import smafa_b200
+from oracle import c_oracle
+from smafa_b200 import synth
+from smafa_b200.dist import ShardedSearcher, shard_bounds
+
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+local_rank = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+L = 60
+D, Q = int(os.environ.get("C3_D", "10000000")), int(os.environ.get("C3_Q", "1000000"))
+STEPS = int(os.environ.get("C3_STEPS", "3"))
+
+t0 = time.perf_counter()
+# every rank derives the same db and queries from the fixed seeds and keeps its own row range
+db_sym = synth.make_db(D, L=L)
+q = synth.pack_symbols(synth.make_queries(db_sym, Q))
+lo, hi = shard_bounds(D, world, rank)
+if rank == 0:
+    db = synth.pack_symbols(db_sym)  # rank 0 keeps the whole db for the oracle
+    shard = db[lo:hi]
+else:
+    shard = synth.pack_symbols(db_sym[lo:hi])
+del db_sym
+t_gen = time.perf_counter() - t0
+
+ctx = smafa_b200.Context(local_rank, "auto")
+searcher = ShardedSearcher(ctx, np.ascontiguousarray(shard), L, world_size=world, rank=rank, presharded=True,
+                           shard_offset=lo, total_rows=D)
+q_dev = torch.from_numpy(q.view(np.int64)).to(dev)
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+out = {"world": world, "D": D, "Q": Q, "L": L, "generate_s": round(t_gen, 1), "modes": {}}
+ok = True
+pick = np.concatenate([np.arange(24), Q // 2 + np.arange(24), Q - 24 + np.arange(24)])
+for name, m, k, n_check in (("--max-divergence 5", 5, None, 72), ("--max-divergence 5 --max-num-hits 10", 5, 10, 12)):
+    rows = searcher.query_dev(q_dev, m, k)  # warm-up (workspace allocation, NCCL channels)
+    barrier()
+    ms, scan = 0.0, 0.0
+    for _ in range(STEPS):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rows = searcher.query_dev(q_dev, m, k)
+        e1.record()
+        barrier()
+        ms += e0.elapsed_time(e1)
+        scan += searcher.last_stats["scan_ms"]
+    t = torch.tensor([ms / STEPS, scan / STEPS], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    got = rows.cpu().numpy().view(np.uint32)
+    if rank == 0:
+        sel = pick[:n_check]
+        want = c_oracle.query(db, L, q[sel], L, m, k, None, threads=os.cpu_count() or 1)
+        want[:, 0] = sel[want[:, 0]]
+        sub = got[np.isin(got[:, 0], sel)]
+        same = sub.shape == want.shape and bool((sub == want).all())
+        order = bool((np.diff(got[:, 0].astype(np.int64)) >= 0).all()) and bool((got[:, 2] <= m).all())
+        x = np.bitwise_count(db[got[:, 1]] ^ q[got[:, 0]]).sum(axis=1) // 2
+        exact = bool((x == got[:, 2]).all())
+        ok = ok and same and order and exact
+        out["modes"][name] = {
+            "ms_per_step": float(t[0]), "scan_ms_max_over_ranks": float(t[1]),
+            "comparisons_per_s": Q * D / (float(t[0]) / 1e3), "rows": int(got.shape[0]),
+            "oracle_subsample_queries": int(n_check), "subsample_identical": same, "order_and_bound_ok": order,
+            "distances_rederived_ok": exact}
+flag = torch.tensor([1 if ok else 0], device=dev)
+if world > 1:
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    out["ok"] = bool(flag.item())
+    print(json.dumps(out))
+searcher.close()
+ctx.close()
+if world > 1:
+    dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)

@@ -643,8 +643,9 @@ extern "C" int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_
   uint64_t total = 0;
   rc = run_range(ctx, db, q_enc_dev, 0, Q, 0, plan, s, stats, [&](uint64_t rows) -> int {
     if (rows && hits_dev && total + rows <= hits_capacity) {
+      // stream-ordered: the next batch's finalize (the next writer of ctx->hits) queues behind this copy, and the
+      // event wait at the end of the call covers the last one
       cudaError_t e = cudaMemcpyAsync(hits_dev + total, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToDevice, s);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2D of hits: %s", cudaGetErrorString(e));
     }
     total += rows;
@@ -688,8 +689,8 @@ extern "C" int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n,
   CU(cudaGetLastError());
   if (hbad) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_merge_dev: query index >= 2^20 or distance >= 4096 in one call");
   uint64_t rows = ctx->h_scalars[1];
+  // stream-ordered like any *_dev result: valid for work queued on `stream` after this call
   CU(cudaMemcpyAsync(cands_dev, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToDevice, s));
-  CU(cudaStreamSynchronize(s));
   *n_out = rows;
   return SMAFA_OK;
 }

@@ -28,46 +28,64 @@ def _pow2_at_least(n):
     return 1 << max(0, int(n) - 1).bit_length()
 
 
-def exchange_candidates(local_rows, group=None, capacity=None):
+class _ExchangeBuffers:
+    """Send block and receive area of the candidate all-gather, kept between steps (allocating and zero-filling
+    them every step showed up as launches in front of the collective)."""
+
+    def __init__(self):
+        self.cap, self.block, self.gathered = 0, None, None
+
+    def get(self, cap, ws, dev):
+        if self.cap != cap or self.block is None or self.block.device != dev:
+            self.block = torch.zeros((cap + 1, 3), dtype=torch.int32, device=dev)
+            self.gathered = torch.empty((ws * (cap + 1), 3), dtype=torch.int32, device=dev)
+            self.cap = cap
+        return self.block, self.gathered
+
+
+def exchange_candidates(local_rows, group=None, capacity=None, buffers=None):
     """All-gathers ragged [n_r, 3] int32 candidate blocks; returns (concatenation in rank order,
     largest per-rank count).  ONE collective on the common path: every rank contributes a block of
     `capacity` rows behind a header row holding its true count, so no separate count exchange is
     needed; only if some rank had more rows than `capacity` (seen by every rank in the gathered
-    headers) is the gather repeated with a capacity that fits.  Works on any backend (NCCL on GPUs,
-    gloo in the CPU tests)."""
+    headers) is the gather repeated with a capacity that fits.  Rows of a block beyond its count are
+    stale and never read.  Works on any backend (NCCL on GPUs, gloo in the CPU tests)."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
     n_local = int(local_rows.shape[0])
     if ws == 1:
         return local_rows, n_local
     dev = local_rows.device
     cap = max(int(capacity or 0), 16)
+    buffers = buffers or _ExchangeBuffers()
     while True:
-        block = torch.zeros((cap + 1, 3), dtype=torch.int32, device=dev)
+        block, gathered = buffers.get(cap, ws, dev)
         block[0, 0] = n_local
         keep = min(n_local, cap)
         block[1:1 + keep] = local_rows[:keep]
-        gathered = torch.empty((ws * (cap + 1), 3), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(gathered, block, group=group)
-        gathered = gathered.view(ws, cap + 1, 3)
-        counts = gathered[:, 0, 0].tolist()  # the one host read-back of the exchange
+        view = gathered.view(ws, cap + 1, 3)
+        counts = view[:, 0, 0].tolist()  # the one host read-back of the exchange
         if max(counts) <= cap:
             break
         cap = _pow2_at_least(max(counts))  # identical on every rank: all of them saw the same headers
-    return torch.cat([gathered[r, 1:1 + c] for r, c in enumerate(counts)], dim=0), max(counts)
+    return torch.cat([view[r, 1:1 + c] for r, c in enumerate(counts)], dim=0), max(counts)
 
 
 class ShardedSearcher:
     """Holds this rank's db shard on its GPU and answers replicated query batches."""
 
-    def __init__(self, ctx, db_words, L, world_size=1, rank=0, group=None, hits_capacity=1 << 24, presharded=False):
+    def __init__(self, ctx, db_words, L, world_size=1, rank=0, group=None, hits_capacity=1 << 24, presharded=False,
+                 shard_offset=None, total_rows=None):
         self.ctx, self.L, self.group = ctx, L, group
         self.world_size, self.rank = world_size, rank
         self.W = (L + 11) // 12
         D = db_words.shape[0]
         if presharded:
-            self.lo = sum_lo = rank * D  # equal shards built rank-locally (bench weak scaling)
+            # shards built rank-locally: equal ones (bench weak scaling) unless the caller gives this shard's first
+            # global row and the db's total
+            self.lo = rank * D if shard_offset is None else int(shard_offset)
             shard = db_words
-            self.D_total = D * world_size
+            self.D_total = D * world_size if total_rows is None else int(total_rows)
         else:
             self.lo, hi = shard_bounds(D, world_size, rank)
             shard = db_words[self.lo:hi]
@@ -77,6 +95,7 @@ class ShardedSearcher:
         self.hits = torch.empty((hits_capacity, 3), dtype=torch.int32, device=self.device)
         self.last_stats = None
         self._exchange_cap = 0  # rows per rank in the candidate all-gather (adapts to the workload)
+        self._exchange_buffers = _ExchangeBuffers()
 
     def _local(self, q_dev, m, k):
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -97,14 +116,14 @@ class ShardedSearcher:
             launches += self.last_stats["kernel_launches"]
             if self.world_size > 1:
                 cap = self._exchange_cap or _pow2_at_least(max(4096, 2 * slab.shape[0]))
-                union, biggest = exchange_candidates(rows, self.group, cap)
+                union, biggest = exchange_candidates(rows, self.group, cap, self._exchange_buffers)
                 self._exchange_cap = _pow2_at_least(max(4096, 2 * biggest))
-                union = union.contiguous()
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 n = self.ctx.merge_dev(union.data_ptr(), union.shape[0], max_divergence, max_num_hits, stream=stream)
                 launches += 8
-                rows = union[:n]
-            rows = rows.clone()
+                rows = union[:n]  # a fresh tensor (the concatenation), merged in place
+            else:
+                rows = rows.clone()  # self.hits is overwritten by the next call
             if s0:
                 rows[:, 0] += s0
             out.append(rows)
