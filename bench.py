@@ -38,8 +38,8 @@ D_PER_GPU = 1_000_000
 MAX_DIVERGENCE = 5
 ALPHABET = "nucleotide"
 # dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full)
-MMA_TRAFFIC_BYTES = 230.4e6 + 6.8e6
-MMA_TRAFFIC_SOURCE = ("ncu dram__bytes_read+write, profiles/r01_ncu_mma_v7_summary.txt (algorithmic: 192 MB "
+MMA_TRAFFIC_BYTES = 230.0e6 + 4.9e6
+MMA_TRAFFIC_SOURCE = ("ncu dram__bytes_read+write, profiles/r01_ncu_mma_v8_summary.txt (algorithmic: 192 MB "
                       "db operand tiles + 19 MB query tiles, read once)")
 
 
