@@ -398,7 +398,14 @@ static int guess_bound(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref
 static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
                      const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st) {
   int rc;
-  uint64_t want_cap = ctx->cand_cap_request ? ctx->cand_cap_request : DEFAULT_CAND_CAP;
+  // Candidate rows: a tight bound emits about a row per query, so the workspace starts at 32 rows per query
+  // (1 Mi..32 Mi; a 32 Mi-row workspace is 1.4 GB of cudaMalloc, most of a small run's start-up) and run_range
+  // grows it to what a batch turned out to need.
+  uint64_t want_cap = ctx->cand_cap_request;
+  if (!want_cap) {
+    want_cap = 1ull << 20;
+    while (want_cap < 32ull * Qb && want_cap < DEFAULT_CAND_CAP) want_cap <<= 1;
+  }
   if ((rc = ensure_workspace(ctx, std::max<uint64_t>(want_cap, ctx->ws_cap)))) return rc;
   if ((rc = ensure_buf(ctx, ctx->bound, ctx->bound_cap, (size_t)Qb + 512))) return rc;  // padded: tile-wide vector loads
   const uint32_t hist_stride = (db->L + 1 + 3) / 4 * 4;  // rows 16-byte aligned for the vector scan in emit_candidate
@@ -540,6 +547,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
     break;
   }
   if (st) st->candidates += n_cand;
+  ctx->cand_needed = n_cand;
   if (n_cand > ctx->ws_cap) return RC_OVERFLOW;
   int fl = launch_finalize(ctx->fw, ctx->cand, n_cand, Qb, plan.k_fin, q_base, db->subject_offset, ctx->hits,
                            ctx->ws_cap, ctx->h_scalars + 1, s);
@@ -563,6 +571,13 @@ static int run_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, 
       int rc = run_batch(ctx, db, q_dev + (q0 + done) * db->W, (uint32_t)nb, (uint32_t)(q_base + q0 + done), plan, &rows, s, st);
       if (rc == RC_OVERFLOW) {
         if (st) st->retries++;
+        // the counter kept counting past the capacity, so the need is known (a lower bound of it when the batch
+        // stopped after its first pass): grow to it while that stays reasonable, else split the batch
+        if (!ctx->cand_cap_request && ctx->cand_needed <= MAX_AUTO_CAND_CAP) {
+          int r2 = ensure_workspace(ctx, std::max<uint64_t>(ctx->ws_cap * 2, ctx->cand_needed + ctx->cand_needed / 4));
+          if (r2) return r2;
+          continue;
+        }
         if (nb == 1) {  // a single query can emit at most D rows
           int r2 = ensure_workspace(ctx, std::max<uint64_t>(ctx->ws_cap * 2, db->D + 1024));
           if (r2) return r2;
@@ -741,6 +756,7 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
   cudaStream_t s = ctx->stream;
   const uint32_t W = words_for(L);
   smafa_db *cdb = nullptr, *bdb = nullptr;
+  const auto t_setup = std::chrono::steady_clock::now();
   int rc = smafa_db_upload(ctx, nullptr, 0, L, 0, &cdb);
   if (!rc) rc = smafa_db_upload(ctx, nullptr, 0, L, 0, &bdb);
   // The centroid set can only grow to n rows (~264 B each with all three images): reserving it up front avoids
@@ -755,7 +771,7 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
 
   // SMAFA_TIMING=1: where the wall time of the greedy goes (host clock, stderr)
   const bool timing = getenv("SMAFA_TIMING") != nullptr;
-  double t_stage[5] = {0, 0, 0, 0, 0};  // batch upload, scan vs centroids, scan in-batch, host replay, centroid append
+  double t_stage[7] = {0, 0, 0, 0, 0, 0, 0};  // batch upload, scan vs centroids, scan in-batch, host replay, centroid append, set-up, tear-down
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto tick = now();
   auto lap = [&](int i) {
@@ -764,6 +780,7 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
     tick = n;
   };
   uint64_t n_batches = 0;
+  t_stage[5] = std::chrono::duration<double, std::milli>(tick - t_setup).count();
 
   QueryPlan plan_old{MODE_MIN, 1, 1, (int)std::min<uint32_t>(t, L)};
   QueryPlan plan_in{MODE_FIXED, 0, UINT32_MAX, (int)std::min<uint32_t>(t, L)};
@@ -843,18 +860,20 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
     lap(4);
     b0 += B;
   }
-  if (timing)
-    fprintf(stderr, "[smafa timing] cluster: %llu batches; batch upload %.1f ms, scan vs centroids %.1f ms, scan in-batch %.1f ms, "
-                    "host replay %.1f ms, centroid append %.1f ms\n",
-            (unsigned long long)n_batches, t_stage[0], t_stage[1], t_stage[2], t_stage[3], t_stage[4]);
   cudaEventRecord(ctx->ev[3], s);
   cudaEventSynchronize(ctx->ev[3]);
   if (stats) {
     cudaEventElapsedTime(&stats->total_ms, ctx->ev[2], ctx->ev[3]);
     stats->pairs = pairs;
   }
+  tick = now();
   if (cdb) smafa_db_free(cdb);
   if (bdb) smafa_db_free(bdb);
+  lap(6);
+  if (timing)
+    fprintf(stderr, "[smafa timing] cluster: %llu batches; set-up %.1f ms, batch upload %.1f ms, scan vs centroids %.1f ms, "
+                    "scan in-batch %.1f ms, host replay %.1f ms, centroid append %.1f ms, tear-down %.1f ms\n",
+            (unsigned long long)n_batches, t_stage[5], t_stage[0], t_stage[1], t_stage[2], t_stage[3], t_stage[4], t_stage[6]);
   if (rc == SMAFA_E_CUDA && ctx->err.empty()) fail(ctx, rc, "smafa_cluster: CUDA failure");
   if (rc) return rc;
   if (n_centroids) *n_centroids = cent_input.size();

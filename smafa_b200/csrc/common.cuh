@@ -89,6 +89,64 @@ __device__ __forceinline__ void emit_candidate(const ScanParams &p, uint32_t q, 
   tighten_bound(p, q, d, bound);
 }
 
+// Smallest t < bound with #(d <= t) >= k in the histogram row h (bound itself when there is none).
+// SMAFA_KTH_SCAN_ATTR: the POPC kernels keep this out of line (scan_popc.cu) -- inlined into their slow path it
+// doubled the registers the hot loop has to save around the call.
+#ifndef SMAFA_KTH_SCAN_ATTR
+#define SMAFA_KTH_SCAN_ATTR __forceinline__
+#endif
+__device__ SMAFA_KTH_SCAN_ATTR int kth_scan(const uint32_t *h, int bound, uint32_t k) {
+  uint32_t cum = 0;
+  int nb = bound;
+  const int nvec = (bound + 3) >> 2;  // covers bins [0, bound)
+  const uint4 *hv = reinterpret_cast<const uint4 *>(h);
+#ifdef SMAFA_KTH_SCAN_SMALL
+  // Register-lean form for kernels whose hot loop is register bound (scan_popc.cu): one 16-byte load at a time.
+  if (nvec <= 16) {
+    for (int v = 0; v < nvec; ++v) {
+      const uint4 c = __ldcg(hv + v);
+      const uint32_t s0 = cum + c.x, s1 = s0 + c.y, s2 = s1 + c.z, s3 = s2 + c.w;
+      if (s3 >= k) {
+        const int t = v * 4 + (s0 >= k ? 0 : (s1 >= k ? 1 : (s2 >= k ? 2 : 3)));
+        if (t < bound) nb = t;
+        break;
+      }
+      cum = s3;
+    }
+  } else
+#endif
+  if (nvec <= 16) {
+    // 16 bins (four independent 16-byte loads) per round trip, stopping at the crossing bin: tight bounds --
+    // the common case -- need one trip, and only 16 registers are live
+    bool open = true;  // the crossing bin has not been reached yet
+#pragma unroll 1
+    for (int v0 = 0; v0 < nvec && open; v0 += 4) {
+      uint4 c[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c[v] = v0 + v < nvec ? __ldcg(hv + v0 + v) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (open && v0 + v < nvec) {
+          const uint32_t s0 = cum + c[v].x, s1 = s0 + c[v].y, s2 = s1 + c[v].z, s3 = s2 + c[v].w;
+          if (s3 >= k) {
+            // bins >= bound of the last vector may hold stale emissions: a crossing there tightens nothing
+            const int t = (v0 + v) * 4 + (s0 >= k ? 0 : (s1 >= k ? 1 : (s2 >= k ? 2 : 3)));
+            if (t < bound) nb = t;
+            open = false;
+          }
+          cum = s3;
+        }
+      }
+    }
+  } else {  // long windows (generic kernel only)
+    for (int t = 0; t < bound; ++t) {
+      cum += __ldcg(h + t);
+      if (cum >= k) { nb = t; break; }
+    }
+  }
+  return nb;
+}
+
 __device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, int d, int &bound) {
   if (p.mode == MODE_MIN) {
     if (d < bound) {
@@ -102,36 +160,7 @@ __device__ __forceinline__ void tighten_bound(const ScanParams &p, uint32_t q, i
     // Only a candidate strictly below the bound can lower it (the bound drops to t < bound once
     // #(d <= t) >= k); ties AT the bound -- the common case -- skip the scan.
     if (d < bound) {
-      uint32_t cum = 0;
-      int nb = bound;
-      const int nvec = (bound + 3) >> 2;  // covers bins [0, bound)
-      const uint4 *hv = reinterpret_cast<const uint4 *>(h);
-      if (nvec <= 16) {
-        // all bins below the bound in ONE round trip: up to 16 independent 16-byte loads are issued
-        // before any of them is consumed
-        uint4 c[16];
-#pragma unroll
-        for (int v = 0; v < 16; ++v) c[v] = v < nvec ? __ldcg(hv + v) : make_uint4(0, 0, 0, 0);
-        bool open = true;  // the crossing bin has not been reached yet
-#pragma unroll
-        for (int v = 0; v < 16; ++v) {
-          if (open && v < nvec) {
-            const uint32_t s0 = cum + c[v].x, s1 = s0 + c[v].y, s2 = s1 + c[v].z, s3 = s2 + c[v].w;
-            if (s3 >= p.k) {
-              // bins >= bound of the last vector may hold stale emissions: a crossing there tightens nothing
-              const int t = v * 4 + (s0 >= p.k ? 0 : (s1 >= p.k ? 1 : (s2 >= p.k ? 2 : 3)));
-              if (t < bound) nb = t;
-              open = false;
-            }
-            cum = s3;
-          }
-        }
-      } else {  // long windows (generic kernel only)
-        for (int t = 0; t < bound; ++t) {
-          cum += __ldcg(h + t);
-          if (cum >= p.k) { nb = t; break; }
-        }
-      }
+      const int nb = kth_scan(h, bound, p.k);
       if (nb < bound) {
         bound = nb;
         atomicMin(p.bound + q, nb);

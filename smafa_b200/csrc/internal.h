@@ -6,7 +6,8 @@
 
 #include "kernels.h"
 
-constexpr uint64_t DEFAULT_CAND_CAP = 32ull << 20;  // candidate rows per batch (8 B each)
+constexpr uint64_t DEFAULT_CAND_CAP = 32ull << 20;     // largest candidate workspace allocated up front (rows, 8 B keys)
+constexpr uint64_t MAX_AUTO_CAND_CAP = 256ull << 20;  // largest the workspace grows to on its own before a batch is split
 
 struct smafa_ctx {
   int device = 0;
@@ -28,6 +29,7 @@ struct smafa_ctx {
   std::string err;
   // candidate + finalize workspace
   uint64_t cand_cap_request = 0;
+  uint64_t cand_needed = 0;      // candidate rows the last batch emitted (may exceed ws_cap: overflow)
   uint64_t ws_cap = 0;
   uint64_t *cand = nullptr;
   smafa::FinalizeWorkspace fw;

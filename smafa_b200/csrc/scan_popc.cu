@@ -12,6 +12,8 @@
 //    this is again a lower bound) -- one POPC per pair when --max-divergence is small;
 //  * grid = query tiles x db chunks, chunk-major, so co-resident blocks stream the same db chunk
 //    (L2/L1 hits) and later chunks start from bounds tightened by earlier ones.
+#define SMAFA_KTH_SCAN_ATTR __noinline__
+#define SMAFA_KTH_SCAN_SMALL
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,9 +45,13 @@ __device__ __forceinline__ Planes<PW> load_row(const uint32_t *__restrict__ base
 // Out-of-line slow path; returns the tightened bound (by value, so the bounds stay in registers).
 // For protein windows `d` is the distance of the 4-class filter image (a lower bound): the exact distance is
 // taken from the symbol words here.
+// The alphabet is a template parameter of the kernel and of this function: with a run-time branch the 64-bit word
+// loop of the protein case raised the registers the nucleotide hot loop has to save around the call (64 -> 160
+// bytes of spills per thread, 4.3e12 -> 2.2e12 comparisons/s at --max-divergence 5).
+template <bool AA>
 __device__ __noinline__ int popc_hit(const ScanParams *p, uint32_t q, uint32_t j, int d, int bound) {
-  if (p->alphabet != ALPHA_NUC) {
-    d = ref_distance(p->q_ref + (size_t)q * p->W, p->d_ref + (size_t)j * p->W, p->W, p->alphabet);
+  if constexpr (AA) {
+    d = ref_distance(p->q_ref + (size_t)q * p->W, p->d_ref + (size_t)j * p->W, p->W, ALPHA_AA);
     if (d > bound) return bound;
   }
   emit_candidate(*p, q, j, d, bound);
@@ -56,7 +62,7 @@ __device__ __noinline__ int popc_hit(const ScanParams *p, uint32_t q, uint32_t j
 // H/Lo planes), so  popc((H^H')|(Lo^Lo')) <= distance  with equality unless exactly one side has
 // an N at a position where the other has A.  A pair whose lower bound already exceeds the query's
 // bound is rejected with 2 LOP3 + 1 POPC per 32 positions; survivors get the exact 3-plane distance.
-template <int PW, int R, bool EARLY>
+template <int PW, int R, bool EARLY, bool AA>
 __global__ void __launch_bounds__(POPC_THREADS, 3) scan_popc_kernel(const __grid_constant__ ScanParams p, uint32_t n_qtiles, uint32_t chunk) {
   constexpr int ROW4 = PW;                      // uint4 per row
   constexpr int FW = (PW == 2 && !EARLY) ? 2 : 1;  // plane words examined by the fast path
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(POPC_THREADS, 3) scan_popc_kernel(const __grid
 #pragma unroll
                 for (int x = 0; x < PW; ++x)
                   dist += __popc((q[r].h[x] ^ d.h[x]) | (q[r].l[x] ^ d.l[x]) | (q[r].n[x] ^ d.n[x]));
-                if (dist <= bound[r]) bound[r] = popc_hit(&p, qi[r], t0 + w + u, dist, bound[r]);
+                if (dist <= bound[r]) bound[r] = popc_hit<AA>(&p, qi[r], t0 + w + u, dist, bound[r]);
               }
             }
           }
@@ -335,7 +341,8 @@ template <int PW, int R, bool EARLY>
 static void launch_one(const ScanParams &p, uint32_t chunk, cudaStream_t s) {
   uint32_t n_qtiles = (p.Q + POPC_THREADS * R - 1) / (POPC_THREADS * R);
   uint32_t n_chunks = (p.d_end - p.d_begin + chunk - 1) / chunk;
-  scan_popc_kernel<PW, R, EARLY><<<n_qtiles * n_chunks, POPC_THREADS, 0, s>>>(p, n_qtiles, chunk);
+  if (p.alphabet == ALPHA_NUC) scan_popc_kernel<PW, R, EARLY, false><<<n_qtiles * n_chunks, POPC_THREADS, 0, s>>>(p, n_qtiles, chunk);
+  else scan_popc_kernel<PW, R, EARLY, true><<<n_qtiles * n_chunks, POPC_THREADS, 0, s>>>(p, n_qtiles, chunk);
 }
 
 // chunk: windows per block, a multiple of POPC_TILE.

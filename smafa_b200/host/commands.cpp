@@ -320,7 +320,10 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
-    // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48)
+    // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48).  Equal
+    // encodings hash alike, so the records are partitioned by hash and every host thread de-duplicates its own
+    // partitions in input order; the survivors are then gathered in input order.  The result does not depend on
+    // the thread count (a record survives iff no earlier record has its encoding).
     struct Key {
       const uint64_t *w;
       uint32_t W;
@@ -333,18 +336,56 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
         return (size_t)h;
       }
     };
-    std::unordered_set<Key, KeyHash> seen;
-    seen.reserve(in.n_ok * 2 + 1);
-    std::vector<uint32_t> uniq;  // record index of each unique encoding, input order
-    std::vector<uint64_t> uwords;
-    uwords.reserve(in.n_ok * (size_t)in.W);
-    for (size_t i = 0; i < in.n_ok; ++i) {
-      Key k{in.words.data() + i * in.W, in.W};
-      if (seen.insert(k).second) {
-        uniq.push_back((uint32_t)i);
-        uwords.insert(uwords.end(), k.w, k.w + in.W);
+    const size_t n_rec = in.n_ok;
+    const unsigned P = n_rec >= 65536 ? host_threads() : 1;  // partitions
+    std::vector<uint8_t> first(n_rec, 0);
+    if (P == 1) {
+      std::unordered_set<Key, KeyHash> seen;
+      seen.reserve(n_rec * 2 + 1);
+      for (size_t i = 0; i < n_rec; ++i) first[i] = seen.insert(Key{in.words.data() + i * in.W, in.W}).second;
+    } else {
+      // pass 1: partition number of every record; pass 2: per-partition index lists (input order); pass 3: dedup
+      std::vector<uint8_t> part(n_rec);
+      std::vector<std::vector<size_t>> counts(P, std::vector<size_t>(P, 0));  // [chunk][partition]
+      parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; ++c)
+          for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) {
+            const unsigned pt = (unsigned)((KeyHash()(Key{in.words.data() + i * in.W, in.W}) >> 40) % P);
+            part[i] = (uint8_t)pt;
+            counts[c][pt]++;
+          }
+      });
+      std::vector<std::vector<uint32_t>> members(P);
+      std::vector<std::vector<size_t>> offset(P, std::vector<size_t>(P, 0));  // [chunk][partition] start inside members
+      for (unsigned pt = 0; pt < P; ++pt) {
+        size_t tot = 0;
+        for (unsigned c = 0; c < P; ++c) { offset[c][pt] = tot; tot += counts[c][pt]; }
+        members[pt].resize(tot);
       }
+      parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; ++c) {
+          std::vector<size_t> at = offset[c];
+          for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) members[part[i]][at[part[i]]++] = (uint32_t)i;
+        }
+      });
+      parallel_chunks(P, 1, [&](unsigned, size_t p0, size_t p1) {
+        for (size_t pt = p0; pt < p1; ++pt) {
+          std::unordered_set<Key, KeyHash> seen;
+          seen.reserve(members[pt].size() * 2 + 1);
+          for (uint32_t i : members[pt]) first[i] = seen.insert(Key{in.words.data() + (size_t)i * in.W, in.W}).second;
+        }
+      });
     }
+    std::vector<uint32_t> uniq;  // record index of each unique encoding, input order
+    size_t n_uniq = 0;
+    for (size_t i = 0; i < n_rec; ++i) n_uniq += first[i];
+    uniq.reserve(n_uniq);
+    for (size_t i = 0; i < n_rec; ++i)
+      if (first[i]) uniq.push_back((uint32_t)i);
+    std::vector<uint64_t> uwords(n_uniq * (size_t)in.W);
+    parallel_chunks(n_uniq, 65536, [&](unsigned, size_t u0, size_t u1) {
+      for (size_t u = u0; u < u1; ++u) memcpy(uwords.data() + u * in.W, in.words.data() + (size_t)uniq[u] * in.W, in.W * sizeof(uint64_t));
+    });
     tm.lap("cluster: encode + de-duplicate");
     std::vector<uint32_t> cof(uniq.size());
     uint64_t n_centroids = 0;
@@ -353,15 +394,28 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
       if (r) { smafa_set_global_error(smafa_last_error(ctx)); return r; }
     }
     tm.lap("cluster: greedy (GPU distances)");
+    // src/cluster.rs:79-84: raw input sequence, decoded centroid.  Formatted on all host threads into per-chunk
+    // buffers and written in order, like the query TSV.
     FdWriter out(out_fd);
-    std::string dec(in.L, '\0');
-    for (size_t u = 0; u < uniq.size(); ++u) {  // src/cluster.rs:79-84: raw input, decoded centroid
-      decode_window(uwords.data() + (size_t)cof[u] * in.W, in.L, dec.data(), alphabet);
-      out.buf.append(in.records[uniq[u]].seq); out.buf.push_back('\t');
-      out.buf.append(dec); out.buf.push_back('\n');
-      out.maybe_flush();
+    const unsigned T = uniq.size() >= 65536 ? host_threads() : 1;
+    std::vector<std::string> parts(T);
+    parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+      for (size_t t = t0; t < t1; ++t) {
+        std::string buf, dec(in.L, '\0');
+        const size_t u0 = uniq.size() * t / T, u1 = uniq.size() * (t + 1) / T;
+        buf.reserve((u1 - u0) * (2 * (size_t)in.L + 2));
+        for (size_t u = u0; u < u1; ++u) {
+          decode_window(uwords.data() + (size_t)cof[u] * in.W, in.L, dec.data(), alphabet);
+          buf.append(in.records[uniq[u]].seq); buf.push_back('\t');
+          buf.append(dec); buf.push_back('\n');
+        }
+        parts[t] = std::move(buf);
+      }
+    });
+    for (std::string &part : parts) {
+      out.buf = std::move(part);
+      out.flush();
     }
-    out.flush();
     tm.lap("cluster: format + write");
     if (in.failed) throw Panic(in.failure);
     return SMAFA_OK;

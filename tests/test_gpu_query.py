@@ -284,6 +284,33 @@ def test_cluster_matches_oracle(ctx, L, t, n, kernel):
     assert (cof.astype(np.int64) == remap[want_cof[keep]]).all()
 
 
+def test_cluster_cli_parallel_host_stages(ctx, tmp_path):
+    """`smafa cluster` end to end on 120 k sequences (10 % duplicate encodings, some in lower case / IUPAC): enough
+    records for the multi-threaded de-duplication and output formatting; stdout must equal the oracle CLI's and must
+    not depend on the number of host threads."""
+    L, n = 60, 120_000
+    sym = synth.make_cluster_input(n, L=L, seed=77, dup_fraction=0.10)
+    seqs = synth.to_ascii(sym)
+    seqs[5] = seqs[5].lower()                      # same encoding as seqs[5] upper-cased
+    seqs[11] = seqs[11].replace(b"N", b"R")          # IUPAC ambiguity encodes like N
+    fa = tmp_path / "in.fna"
+    synth.write_fasta(fa, seqs)
+    want = subprocess.run([c_oracle.CLI, "cluster", "-i", str(fa), "-d", "3"], capture_output=True, text=True)
+    assert want.returncode == 0, want.stderr
+    outs = []
+    for threads in ("1", "3", ""):
+        env = dict(os.environ)
+        if threads:
+            env["SMAFA_HOST_THREADS"] = threads
+        else:
+            env.pop("SMAFA_HOST_THREADS", None)
+        r = subprocess.run([api.CLI_PATH, "cluster", "-i", str(fa), "-d", "3"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == want.stdout
+    assert outs[1] == outs[0] and outs[2] == outs[0]
+
+
 # ---- optimistic first pass under a guessed bound (csrc/guess.cu) -----------------------------------
 
 @pytest.mark.parametrize("kernel", KERNELS)
