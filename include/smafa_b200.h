@@ -182,6 +182,16 @@ int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fast
                      int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
                      int out_fd);
 int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd);
+/* The same two commands for a process that has no context yet (the CLI): the context for `device` is created on a
+ * helper thread while the files are read, decoded and encoded -- CUDA initialisation takes 1-3 s and does not
+ * depend on the inputs.  `kernel` is a smafa_kernel, `alphabet` a smafa_alphabet.  *ctx_out (may be NULL) receives
+ * the context for error reporting and smafa_ctx_destroy; a device that cannot be initialised is an error even
+ * when the inputs turned out to need no device work. */
+int smafa_query_file_on_device(int device, int kernel, int alphabet, const char *db_path, const char *query_fasta,
+                               int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
+                               int out_fd, smafa_ctx **ctx_out);
+int smafa_cluster_file_on_device(int device, int kernel, int alphabet, const char *input_fasta,
+                                 uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out);
 int smafa_count_files(const char *const *paths, size_t n_paths, int out_fd);
 /* Loads a db file into host words (src/lib.rs:206-218: File::open, version gate, postcard decode) -- the
  * LEB128 stream is decoded on all host threads.  *words ([n][W], reference bit layout) is released with

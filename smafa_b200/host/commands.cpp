@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -227,13 +228,68 @@ extern "C" int smafa_db_file_check(const char *db_path) {
   });
 }
 
-// src/lib.rs:198-325
+// A context that may still be under construction on a helper thread: CUDA initialisation takes 1-3 s and does not
+// depend on the inputs, so the CLI entry points (smafa_*_file_on_device) start it first and read, decode and encode
+// the files meanwhile.  get() joins; a failed creation is reported through *rc and the global error text.
+struct LazyCtx {
+  smafa_ctx *ctx = nullptr;
+  int rc = SMAFA_OK;
+  std::string err;
+  std::thread th;
+  void start(int device, int kernel, int alphabet) {
+    th = std::thread([this, device, kernel, alphabet] {
+      rc = smafa_ctx_create(&ctx, device, kernel);
+      if (rc) err = smafa_last_error(nullptr);  // the error text is thread-local: carry it over
+      else smafa_ctx_set_alphabet(ctx, alphabet);
+    });
+  }
+  smafa_ctx *get() {
+    if (th.joinable()) th.join();
+    if (rc) smafa_set_global_error(err);
+    return rc ? nullptr : ctx;
+  }
+  ~LazyCtx() { if (th.joinable()) th.join(); }
+};
+
+static int query_file_impl(LazyCtx &lazy, int alphabet, const char *db_path, const char *query_fasta, int64_t max_divergence,
+                           int64_t max_num_hits, int64_t limit_per_sequence, int out_fd);
+static int cluster_file_impl(LazyCtx &lazy, int alphabet, const char *input_fasta, uint32_t max_divergence, int out_fd);
+
 extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fasta, int64_t max_divergence,
                                 int64_t max_num_hits, int64_t limit_per_sequence, int out_fd) {
+  if (!ctx) { smafa_set_global_error("smafa_query_file needs a context (no CPU fallback)"); return SMAFA_E_PANIC; }
+  LazyCtx lazy;
+  lazy.ctx = ctx;
+  return query_file_impl(lazy, ctx->alphabet, db_path, query_fasta, max_divergence, max_num_hits, limit_per_sequence, out_fd);
+}
+
+extern "C" int smafa_query_file_on_device(int device, int kernel, int alphabet, const char *db_path, const char *query_fasta,
+                                          int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
+                                          int out_fd, smafa_ctx **ctx_out) {
+  LazyCtx lazy;
+  lazy.start(device, kernel, alphabet);
+  int rc = query_file_impl(lazy, alphabet, db_path, query_fasta, max_divergence, max_num_hits, limit_per_sequence, out_fd);
+  smafa_ctx *ctx = lazy.get();  // also when the inputs needed no device work: a missing GPU is reported, not ignored
+  if (ctx_out) *ctx_out = ctx; else if (ctx) smafa_ctx_destroy(ctx);
+  return rc ? rc : lazy.rc;
+}
+
+extern "C" int smafa_cluster_file_on_device(int device, int kernel, int alphabet, const char *input_fasta,
+                                            uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out) {
+  LazyCtx lazy;
+  lazy.start(device, kernel, alphabet);
+  int rc = cluster_file_impl(lazy, alphabet, input_fasta, max_divergence, out_fd);
+  smafa_ctx *ctx = lazy.get();
+  if (ctx_out) *ctx_out = ctx; else if (ctx) smafa_ctx_destroy(ctx);
+  return rc ? rc : lazy.rc;
+}
+
+// src/lib.rs:198-325
+static int query_file_impl(LazyCtx &lazy, int alphabet, const char *db_path, const char *query_fasta, int64_t max_divergence,
+                           int64_t max_num_hits, int64_t limit_per_sequence, int out_fd) {
   smafa_db *dbh = nullptr;
+  smafa_ctx *ctx = nullptr;
   int rc = guarded([&]() -> int {
-    if (!ctx) throw Panic("smafa_query_file needs a context (no CPU fallback)");
-    const int alphabet = ctx->alphabet;
     StageTimer tm;
     WindowDb db = parse_db(read_file(db_path));  // File::open(..)? -> Err, version gate -> panic
     tm.lap("query: read + decode db");
@@ -248,6 +304,8 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
     const bool mode_b = max_num_hits >= 0 && max_num_hits != 1;  // src/lib.rs:224
     FdWriter out(out_fd);
     if (in.n_ok > 0) {
+      if (!(ctx = lazy.get())) return lazy.rc;
+      tm.lap("query: wait for the CUDA context");
       int r = smafa_db_upload(ctx, db.words.data(), db.n, db.L, 0, &dbh);
       if (r) return r;
       tm.lap("query: db upload + re-pack");
@@ -303,11 +361,17 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
   return rc;
 }
 
-// src/cluster.rs:13-94
 extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd) {
+  if (!ctx) { smafa_set_global_error("smafa_cluster_file needs a context (no CPU fallback)"); return SMAFA_E_PANIC; }
+  LazyCtx lazy;
+  lazy.ctx = ctx;
+  return cluster_file_impl(lazy, ctx->alphabet, input_fasta, max_divergence, out_fd);
+}
+
+// src/cluster.rs:13-94
+static int cluster_file_impl(LazyCtx &lazy, int alphabet, const char *input_fasta, uint32_t max_divergence, int out_fd) {
   return guarded([&]() -> int {
-    if (!ctx) throw Panic("smafa_cluster_file needs a context (no CPU fallback)");
-    const int alphabet = ctx->alphabet;
+    smafa_ctx *ctx = nullptr;
     StageTimer tm;
     std::vector<Record> recs = read_fastx(input_fasta);
     tm.lap("cluster: read FASTX");
@@ -390,6 +454,8 @@ extern "C" int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint3
     std::vector<uint32_t> cof(uniq.size());
     uint64_t n_centroids = 0;
     if (!uniq.empty()) {
+      if (!(ctx = lazy.get())) return lazy.rc;
+      tm.lap("cluster: wait for the CUDA context");
       int r = smafa_cluster(ctx, uwords.data(), uniq.size(), in.L, max_divergence, cof.data(), &n_centroids, nullptr, nullptr);
       if (r) { smafa_set_global_error(smafa_last_error(ctx)); return r; }
     }

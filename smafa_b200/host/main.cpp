@@ -117,13 +117,11 @@ int main(int argc, char **argv) {
     fprintf(stderr, "[smafa timing] %-28s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
     t0 = now;
   };
+  // the context is created on a helper thread while the inputs are read and encoded (SMAFA_TIMING shows the wait)
   smafa_ctx *ctx = nullptr;
-  int rc = smafa_ctx_create(&ctx, (int)device, kernel);
-  if (rc) return finish(rc, nullptr);
-  lap("CUDA init + context");
-  smafa_ctx_set_alphabet(ctx, alphabet);
-  if (is_query) rc = smafa_query_file(ctx, database, query, m, k, r, 1);
-  else rc = smafa_cluster_file(ctx, input, (uint32_t)m, 1);
+  int rc;
+  if (is_query) rc = smafa_query_file_on_device((int)device, kernel, alphabet, database, query, m, k, r, 1, &ctx);
+  else rc = smafa_cluster_file_on_device((int)device, kernel, alphabet, input, (uint32_t)m, 1, &ctx);
   lap(is_query ? "query (all stages above)" : "cluster (all stages above)");
   int code = finish(rc, ctx);
   smafa_ctx_destroy(ctx);
