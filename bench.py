@@ -337,7 +337,9 @@ def main():
             "dtype": "s8" if st["kernel_used"] == 2 else "u32-popcount", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "kernel": {1: "popc", 2: "mma", 0: "generic"}[st["kernel_used"]],
                        "l2": "flushed between timed steps (256 MiB write)", "hit_rows": int(n_rows),
-                       "candidates_per_step": int(st["candidates"]), "parallelism": f"db-row-shard x{world}"},
+                       "candidates_per_step": int(st["candidates"]), "parallelism": f"db-row-shard x{world}",
+                       # selection without a useful bound scans under a guessed bound first (csrc/guess.cu)
+                       "guess_bound": int(st["guess_bound"]), "rescanned_queries": int(st["rescanned"])},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "comparisons/s",
                     "h2d_bytes_per_step": int(q.nbytes) * world, "d2h_bytes_per_step": int(host_rows.nbytes)},

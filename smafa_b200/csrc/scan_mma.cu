@@ -674,8 +674,11 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
                                     int need0, int alphabet, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
   const bool aa_exact = enc == MMA_ENC_AA;
   const uint32_t chunks = KB / 16, PB = aa_exact ? MMA_AA_POS : KB / enc, gap = PB - L;
+  // thread -> (row, k-chunk): eight consecutive threads take the eight rows of one core-matrix column, whose 16-byte
+  // pieces are contiguous in the tile image (128-byte stores instead of 16-byte ones 128 bytes apart)
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t row = row_begin + (uint32_t)(idx / chunks), c = (uint32_t)(idx % chunks);
+  const uint32_t t = (uint32_t)(idx % (8 * chunks));
+  const uint32_t row = row_begin + (uint32_t)(idx / (8 * chunks)) * 8 + (t & 7), c = t >> 3;
   if (row >= row_end) return;
   const bool valid = row < n_valid, had = enc <= 3;
   const uint64_t *w = ref + (size_t)row * W;
@@ -756,7 +759,7 @@ static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t 
                                 uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query, int need0,
                                 int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s) {
   if (row_end <= row_begin) return;
-  const uint64_t n = (uint64_t)(row_end - row_begin) * (KB / 16);
+  const uint64_t n = (uint64_t)((row_end - row_begin + 7) / 8) * 8 * (KB / 16);
   pack_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
                                                                 enc, is_query, need0, alphabet, meta, out);
 }

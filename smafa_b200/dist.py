@@ -10,6 +10,9 @@ merged (distance, subject) order equals the reference's print order (src/lib.rs:
 torch / torch.distributed are plumbing only (device buffers, streams, NCCL); the scan and the
 merge are the library's own kernels (smafa_query_dev / smafa_merge_dev).
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -96,6 +99,8 @@ class ShardedSearcher:
         self.last_stats = None
         self._exchange_cap = 0  # rows per rank in the candidate all-gather (adapts to the workload)
         self._exchange_buffers = _ExchangeBuffers()
+        self._timing = bool(os.environ.get("SMAFA_TIMING"))
+        self.phase_ms = [0.0, 0.0, 0.0]  # local scan + selection, candidate exchange, merge (SMAFA_TIMING=1)
 
     def _local(self, q_dev, m, k):
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -110,18 +115,30 @@ class ShardedSearcher:
         identical on every rank."""
         out = []
         launches = 0
+        timing = self._timing
         for s0 in range(0, q_dev.shape[0], MAX_SLAB):
             slab = q_dev[s0:s0 + MAX_SLAB]
+            t0 = time.perf_counter()
             rows = self._local(slab, max_divergence, max_num_hits)
             launches += self.last_stats["kernel_launches"]
             if self.world_size > 1:
+                if timing:
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
                 cap = self._exchange_cap or _pow2_at_least(max(4096, 2 * slab.shape[0]))
                 union, biggest = exchange_candidates(rows, self.group, cap, self._exchange_buffers)
                 self._exchange_cap = _pow2_at_least(max(4096, 2 * biggest))
+                if timing:
+                    torch.cuda.synchronize()
+                    t2 = time.perf_counter()
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 n = self.ctx.merge_dev(union.data_ptr(), union.shape[0], max_divergence, max_num_hits, stream=stream)
                 launches += 8
                 rows = union[:n]  # a fresh tensor (the concatenation), merged in place
+                if timing:  # SMAFA_TIMING=1: host clock per phase (with a device sync after each: measurement aid only)
+                    torch.cuda.synchronize()
+                    t3 = time.perf_counter()
+                    self.phase_ms = [x + 1e3 * y for x, y in zip(self.phase_ms, (t1 - t0, t2 - t1, t3 - t2))]
             else:
                 rows = rows.clone()  # self.hits is overwritten by the next call
             if s0:
