@@ -311,6 +311,32 @@ def test_cluster_cli_parallel_host_stages(ctx, tmp_path):
     assert outs[1] == outs[0] and outs[2] == outs[0]
 
 
+# ---- tcgen05 kernel under candidate pressure: survivor rings, verifier warps, flood path ----------------
+
+def test_mma_survivor_rings_under_pressure(ctx):
+    """Dense survivor patterns for the tcgen05 kernel (>= 64 queries, so AUTO/MMA really runs it): (a) every pair
+    survives -- the epilogue's flood path verifies straight from the masks; (b) big families under a loose bound --
+    tens of survivors per 64-column chunk, so the per-warp rings fill faster than the verifier warps drain them and
+    the epilogue has to wait for room; (c) the same with the k-th tightening active."""
+    L = 60
+    ctx.set_kernel("mma")
+    one = synth.random_symbols(1, L, seed=21)
+    same = synth.pack_symbols(np.repeat(one, 1500, axis=0))
+    q_sym = np.repeat(one, 320, axis=0)
+    q_sym[::4] = synth.random_symbols(len(q_sym[::4]), L, seed=22)
+    q = synth.pack_symbols(q_sym)
+    for m, k in [(None, None), (0, None), (None, 3), (4, 2000), (None, 1499)]:
+        st = check_query(ctx, same, q, L, m, k, None, "mma")            # (a)
+        assert st["kernel_used"] == 2
+    fam = synth.make_db(40_000, L=L, seed=23, family=400, max_subs=6, noise=0.0)
+    qf = synth.make_queries(fam, 512, seed=24, max_subs=4, noise=0.0)
+    dbw, qw = synth.pack_symbols(fam), synth.pack_symbols(qf)
+    for m, k in [(12, 40_000), (14, None), (16, 300), (None, 250)]:
+        st = check_query(ctx, dbw, qw, L, m, k, None, "mma")           # (b), (c)
+        assert st["kernel_used"] == 2
+    assert st["candidates"] >= 250 * 512
+
+
 # ---- optimistic first pass under a guessed bound (csrc/guess.cu) -----------------------------------
 
 @pytest.mark.parametrize("kernel", KERNELS)
