@@ -60,7 +60,10 @@ def barrier():
 out = {"world": world, "D": D, "Q": Q, "L": L, "generate_s": round(t_gen, 1), "modes": {}}
 ok = True
 pick = np.concatenate([np.arange(24), Q // 2 + np.arange(24), Q - 24 + np.arange(24)])
-for name, m, k, n_check in (("--max-divergence 5", 5, None, 72), ("--max-divergence 5 --max-num-hits 10", 5, 10, 12)):
+MODES = [("--max-divergence 5", 5, None, 72), ("--max-divergence 5 --max-num-hits 10", 5, 10, 12)]
+if os.environ.get("C3_UNBOUNDED"):  # the CLI defaults: no --max-divergence (guessed first pass, csrc/guess.cu)
+    MODES += [("(no --max-divergence)", None, None, 72), ("--max-num-hits 10 (no --max-divergence)", None, 10, 12)]
+for name, m, k, n_check in MODES:
     rows = searcher.query_dev(q_dev, m, k)  # warm-up (workspace allocation, NCCL channels)
     barrier()
     ms, scan = 0.0, 0.0
@@ -82,7 +85,7 @@ for name, m, k, n_check in (("--max-divergence 5", 5, None, 72), ("--max-diverge
         want[:, 0] = sel[want[:, 0]]
         sub = got[np.isin(got[:, 0], sel)]
         same = sub.shape == want.shape and bool((sub == want).all())
-        order = bool((np.diff(got[:, 0].astype(np.int64)) >= 0).all()) and bool((got[:, 2] <= m).all())
+        order = bool((np.diff(got[:, 0].astype(np.int64)) >= 0).all()) and bool((got[:, 2] <= (L if m is None else m)).all())
         x = np.bitwise_count(db[got[:, 1]] ^ q[got[:, 0]]).sum(axis=1) // 2
         exact = bool((x == got[:, 2]).all())
         ok = ok and same and order and exact
@@ -90,7 +93,8 @@ for name, m, k, n_check in (("--max-divergence 5", 5, None, 72), ("--max-diverge
             "ms_per_step": float(t[0]), "scan_ms_max_over_ranks": float(t[1]),
             "comparisons_per_s": Q * D / (float(t[0]) / 1e3), "rows": int(got.shape[0]),
             "oracle_subsample_queries": int(n_check), "subsample_identical": same, "order_and_bound_ok": order,
-            "distances_rederived_ok": exact}
+            "distances_rederived_ok": exact, "guess_bound": int(searcher.last_stats["guess_bound"]),
+            "rescanned_queries": int(searcher.last_stats["rescanned"]), "candidates": int(searcher.last_stats["candidates"])}
 flag = torch.tensor([1 if ok else 0], device=dev)
 if world > 1:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
