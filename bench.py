@@ -192,7 +192,8 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
         executed = pairs_per_launch * 2 * mma_k / secs / 1e12
         # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's
         # issue-only tcgen05 kind::i8 probe (smafa_debug_mma_peak) on this GPU, same clocks.
-        return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
+        return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s",
+                "unit_note": "integer path: 1 'FLOP' here = one int8 multiply or add on the tensor pipe (TOP/s)",
                 "frac": achieved / int8_peak, "traffic": MMA_TRAFFIC_BYTES,
                 "peak_source": "measured in this run: tcgen05.mma kind::i8 M128xN256xK32 issue-only probe "
                                f"on all SMs; for reference 2 x {peaks_kind} bf16_tflops = {2 * peaks['bf16_tflops']:.0f}",

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SMAFA_B200_ABI_VERSION 1
+#define SMAFA_B200_ABI_VERSION 2 /* 2: smafa_stats gained guess_bound and rescanned; smafa_*_file_on_device */
 
 typedef enum smafa_status {
   SMAFA_OK = 0,
