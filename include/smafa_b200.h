@@ -181,6 +181,10 @@ int smafa_makedb_file_alphabet(const char *subject_fasta, const char *db_path, i
 int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char *query_fasta,
                      int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
                      int out_fd);
+/* Host helper of cluster: first[i] = 1 iff no earlier window has the encoding of window i -- the
+ * HashSet<Vec<u64>> de-duplication of src/cluster.rs:24,46-48, hash-partitioned over the host threads
+ * (the result does not depend on their number).  smafa_cluster expects exactly the windows with first[i] = 1. */
+int smafa_mark_first_occurrences(const uint64_t *words, uint64_t n, uint32_t W, uint8_t *first);
 int smafa_cluster_file(smafa_ctx *ctx, const char *input_fasta, uint32_t max_divergence, int out_fd);
 /* The same two commands for a process that has no context yet (the CLI): the context for `device` is created on a
  * helper thread while the files are read, decoded and encoded -- CUDA initialisation takes 1-3 s and does not

@@ -228,6 +228,67 @@ extern "C" int smafa_db_file_check(const char *db_path) {
   });
 }
 
+// first[i] = 1 iff no earlier record has the encoding of record i (the HashSet<Vec<u64>> of src/cluster.rs:24,46-48).
+// Equal encodings hash alike, so the records are partitioned by hash and every host thread de-duplicates its own
+// partitions in input order.  The result does not depend on the thread count.
+static void mark_first_occurrences(const uint64_t *words, size_t n_rec, uint32_t W, uint8_t *first) {
+  struct Key {
+    const uint64_t *w;
+    uint32_t W;
+    bool operator==(const Key &o) const { return memcmp(w, o.w, W * sizeof(uint64_t)) == 0; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key &k) const {
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (uint32_t i = 0; i < k.W; ++i) { h ^= k.w[i]; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 31; }
+      return (size_t)h;
+    }
+  };
+  const unsigned P = n_rec >= 65536 ? host_threads() : 1;  // partitions
+  if (P == 1) {
+    std::unordered_set<Key, KeyHash> seen;
+    seen.reserve(n_rec * 2 + 1);
+    for (size_t i = 0; i < n_rec; ++i) first[i] = seen.insert(Key{words + i * W, W}).second;
+    return;
+  }
+  // pass 1: partition number of every record; pass 2: per-partition index lists (input order); pass 3: dedup
+  std::vector<uint8_t> part(n_rec);
+  std::vector<std::vector<size_t>> counts(P, std::vector<size_t>(P, 0));  // [chunk][partition]
+  parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
+    for (size_t c = c0; c < c1; ++c)
+      for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) {
+        const unsigned pt = (unsigned)((KeyHash()(Key{words + i * W, W}) >> 40) % P);
+        part[i] = (uint8_t)pt;
+        counts[c][pt]++;
+      }
+  });
+  std::vector<std::vector<uint32_t>> members(P);
+  std::vector<std::vector<size_t>> offset(P, std::vector<size_t>(P, 0));  // [chunk][partition] start inside members
+  for (unsigned pt = 0; pt < P; ++pt) {
+    size_t tot = 0;
+    for (unsigned c = 0; c < P; ++c) { offset[c][pt] = tot; tot += counts[c][pt]; }
+    members[pt].resize(tot);
+  }
+  parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
+    for (size_t c = c0; c < c1; ++c) {
+      std::vector<size_t> at = offset[c];
+      for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) members[part[i]][at[part[i]]++] = (uint32_t)i;
+    }
+  });
+  parallel_chunks(P, 1, [&](unsigned, size_t p0, size_t p1) {
+    for (size_t pt = p0; pt < p1; ++pt) {
+      std::unordered_set<Key, KeyHash> seen;
+      seen.reserve(members[pt].size() * 2 + 1);
+      for (uint32_t i : members[pt]) first[i] = seen.insert(Key{words + (size_t)i * W, W}).second;
+    }
+  });
+}
+
+extern "C" int smafa_mark_first_occurrences(const uint64_t *words, uint64_t n, uint32_t W, uint8_t *first) {
+  if ((n && (!words || !first)) || W == 0 || n >= (1ull << 32)) return SMAFA_E_INVALID;
+  return guarded([&]() -> int { mark_first_occurrences(words, (size_t)n, W, first); return SMAFA_OK; });
+}
+
 // A context that may still be under construction on a helper thread: CUDA initialisation takes 1-3 s and does not
 // depend on the inputs, so the CLI entry points (smafa_*_file_on_device) start it first and read, decode and encode
 // the files meanwhile.  get() joins; a failed creation is reported through *rc and the global error text.
@@ -384,62 +445,10 @@ static int cluster_file_impl(LazyCtx &lazy, int alphabet, const char *input_fast
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
-    // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48).  Equal
-    // encodings hash alike, so the records are partitioned by hash and every host thread de-duplicates its own
-    // partitions in input order; the survivors are then gathered in input order.  The result does not depend on
-    // the thread count (a record survives iff no earlier record has its encoding).
-    struct Key {
-      const uint64_t *w;
-      uint32_t W;
-      bool operator==(const Key &o) const { return memcmp(w, o.w, W * sizeof(uint64_t)) == 0; }
-    };
-    struct KeyHash {
-      size_t operator()(const Key &k) const {
-        uint64_t h = 0x9E3779B97F4A7C15ull;
-        for (uint32_t i = 0; i < k.W; ++i) { h ^= k.w[i]; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 31; }
-        return (size_t)h;
-      }
-    };
+    // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48)
     const size_t n_rec = in.n_ok;
-    const unsigned P = n_rec >= 65536 ? host_threads() : 1;  // partitions
     std::vector<uint8_t> first(n_rec, 0);
-    if (P == 1) {
-      std::unordered_set<Key, KeyHash> seen;
-      seen.reserve(n_rec * 2 + 1);
-      for (size_t i = 0; i < n_rec; ++i) first[i] = seen.insert(Key{in.words.data() + i * in.W, in.W}).second;
-    } else {
-      // pass 1: partition number of every record; pass 2: per-partition index lists (input order); pass 3: dedup
-      std::vector<uint8_t> part(n_rec);
-      std::vector<std::vector<size_t>> counts(P, std::vector<size_t>(P, 0));  // [chunk][partition]
-      parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
-        for (size_t c = c0; c < c1; ++c)
-          for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) {
-            const unsigned pt = (unsigned)((KeyHash()(Key{in.words.data() + i * in.W, in.W}) >> 40) % P);
-            part[i] = (uint8_t)pt;
-            counts[c][pt]++;
-          }
-      });
-      std::vector<std::vector<uint32_t>> members(P);
-      std::vector<std::vector<size_t>> offset(P, std::vector<size_t>(P, 0));  // [chunk][partition] start inside members
-      for (unsigned pt = 0; pt < P; ++pt) {
-        size_t tot = 0;
-        for (unsigned c = 0; c < P; ++c) { offset[c][pt] = tot; tot += counts[c][pt]; }
-        members[pt].resize(tot);
-      }
-      parallel_chunks(P, 1, [&](unsigned, size_t c0, size_t c1) {
-        for (size_t c = c0; c < c1; ++c) {
-          std::vector<size_t> at = offset[c];
-          for (size_t i = n_rec * c / P; i < n_rec * (c + 1) / P; ++i) members[part[i]][at[part[i]]++] = (uint32_t)i;
-        }
-      });
-      parallel_chunks(P, 1, [&](unsigned, size_t p0, size_t p1) {
-        for (size_t pt = p0; pt < p1; ++pt) {
-          std::unordered_set<Key, KeyHash> seen;
-          seen.reserve(members[pt].size() * 2 + 1);
-          for (uint32_t i : members[pt]) first[i] = seen.insert(Key{in.words.data() + (size_t)i * in.W, in.W}).second;
-        }
-      });
-    }
+    mark_first_occurrences(in.words.data(), n_rec, in.W, first.data());
     std::vector<uint32_t> uniq;  // record index of each unique encoding, input order
     size_t n_uniq = 0;
     for (size_t i = 0; i < n_rec; ++i) n_uniq += first[i];

@@ -82,3 +82,31 @@ def test_first_bad_record_wins_for_every_thread_count(tmp_path):
         assert r.returncode == 101
         outs.append(r.stderr)
     assert outs[0] == outs[1] and 'Byte 33 cannot be interpreted as nucleotide, in sequence "seq40000" at position 10' in outs[0]
+
+
+DEDUP = """
+import sys, ctypes, hashlib, numpy as np
+sys.path.insert(0, %r)
+import smafa_b200
+from smafa_b200 import synth
+lib = smafa_b200.load_library()
+sym = synth.make_cluster_input(150_000, L=60, seed=9, dup_fraction=0.2)
+w = synth.pack_symbols(sym)
+first = np.zeros(w.shape[0], dtype=np.uint8)
+lib.smafa_mark_first_occurrences.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
+assert lib.smafa_mark_first_occurrences(w.ctypes.data, w.shape[0], w.shape[1], first.ctypes.data) == 0
+_, idx = np.unique(w, axis=0, return_index=True)
+want = np.zeros_like(first); want[idx] = 1
+print("OK" if (first == want).all() else "MISMATCH", hashlib.sha256(first.tobytes()).hexdigest(), int(first.sum()))
+""" % ROOT
+
+
+def test_cluster_deduplication_matches_numpy_for_every_thread_count():
+    """src/cluster.rs:46-48 (skip an encoding seen before): the hash-partitioned host pass must mark exactly the first
+    occurrences, whatever the number of host threads."""
+    outs = []
+    for threads in (1, 3, 8, 32):
+        env = dict(os.environ, SMAFA_HOST_THREADS=str(threads))
+        r = subprocess.run([sys.executable, "-c", DEDUP], env=env, capture_output=True, text=True, check=True)
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0].startswith("OK") and len(set(outs)) == 1, outs
