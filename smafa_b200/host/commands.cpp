@@ -79,8 +79,9 @@ struct StageTimer {
 };
 
 struct EncodedInput {
+  FastxFile file;               // owns what the records' views point into
   std::vector<Record> records;
-  std::vector<uint64_t> words;  // [n_ok][W]
+  Words words;                  // [n_ok][W]
   uint32_t W = 0, L = 0;
   size_t n_ok = 0;              // records encoded before the first failure
   bool failed = false;
@@ -90,9 +91,10 @@ struct EncodedInput {
 // Encodes records in order until one cannot be handled.  `expect_len` (0 = take the first
 // record's) is the window length every record must have; `mismatch` builds the panic text.
 template <class MismatchMsg>
-EncodedInput encode_all(std::vector<Record> records, uint32_t expect_len, int alphabet, MismatchMsg mismatch) {
+EncodedInput encode_all(FastxFile file, uint32_t expect_len, int alphabet, MismatchMsg mismatch) {
   EncodedInput in;
-  in.records = std::move(records);
+  in.records = std::move(file.recs);
+  in.file = std::move(file);
   if (in.records.empty()) return in;
   in.L = expect_len ? expect_len : (uint32_t)in.records[0].seq.size();
   in.W = words_for_len(in.L);
@@ -163,14 +165,15 @@ extern "C" int smafa_makedb_file(const char *subject_fasta, const char *db_path)
 extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char *db_path, int alphabet) {
   return guarded([&]() -> int {
     StageTimer tm;
-    std::vector<Record> recs = read_fastx(subject_fasta);
+    FastxFile fx = read_fastx(subject_fasta);
+    std::vector<Record> &recs = fx.recs;
     tm.lap("makedb: read FASTX");
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
       encode_or_panic(recs[0], t.data(), alphabet);
       throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
     }
-    EncodedInput in = encode_all(std::move(recs), 0, alphabet, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(fx), 0, alphabet, [](size_t got, uint32_t want) {
       return "WindowSet seq length is " + std::to_string(want) + ", got a new sequence of length " + std::to_string(got);
     });
     tm.lap("makedb: encode");
@@ -180,7 +183,7 @@ extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char 
     db.W = in.W;
     db.L = in.L;
     db.words = std::move(in.words);
-    const std::vector<uint8_t> bytes = serialize_db(db);
+    const Bytes bytes = serialize_db(db);
     tm.lap("makedb: serialize");
     FILE *f = fopen(db_path, "wb");
     if (!f) throw IoError(std::string("cannot create ") + db_path);
@@ -212,7 +215,7 @@ extern "C" int smafa_db_file_load(const char *db_path, uint64_t **words, uint64_
 // src/lib.rs:208-217: File::open(..)? then the version gate
 extern "C" int smafa_db_file_check(const char *db_path) {
   return guarded([&]() -> int {
-    std::vector<uint8_t> bytes = read_file(db_path);
+    Bytes bytes = read_file(db_path);
     if (bytes.size() > 16) bytes.resize(16);
     if (bytes.size() < 4) throw Panic("range end index 4 out of range for slice of length " + std::to_string(bytes.size()));
     uint64_t v = 0;
@@ -354,10 +357,10 @@ static int query_file_impl(LazyCtx &lazy, int alphabet, const char *db_path, con
     StageTimer tm;
     WindowDb db = parse_db(read_file(db_path));  // File::open(..)? -> Err, version gate -> panic
     tm.lap("query: read + decode db");
-    std::vector<Record> recs = read_fastx(query_fasta);
+    FastxFile fx = read_fastx(query_fasta);
     tm.lap("query: read FASTX");
     // get_distances checks the length only when the db is non-empty (src/lib.rs:72)
-    EncodedInput in = encode_all(std::move(recs), db.L, alphabet, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(fx), db.L, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
@@ -434,14 +437,15 @@ static int cluster_file_impl(LazyCtx &lazy, int alphabet, const char *input_fast
   return guarded([&]() -> int {
     smafa_ctx *ctx = nullptr;
     StageTimer tm;
-    std::vector<Record> recs = read_fastx(input_fasta);
+    FastxFile fx = read_fastx(input_fasta);
+    std::vector<Record> &recs = fx.recs;
     tm.lap("cluster: read FASTX");
     if (!recs.empty() && recs[0].seq.empty()) {
       std::vector<uint64_t> t(1);
       encode_or_panic(recs[0], t.data(), alphabet);
       throw Panic("Cannot add empty sequence to WindowSet: TryFromIntError(())");
     }
-    EncodedInput in = encode_all(std::move(recs), 0, alphabet, [](size_t got, uint32_t want) {
+    EncodedInput in = encode_all(std::move(fx), 0, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
     });
@@ -502,13 +506,14 @@ extern "C" int smafa_count_files(const char *const *paths, size_t n_paths, int o
   return guarded([&]() -> int {
     std::string js = "[";
     for (size_t i = 0; i < n_paths; ++i) {
-      std::vector<Record> recs;
+      FastxFile fx;
       try {
-        recs = read_fastx(paths[i], /*io_error_on_open=*/true);  // parse_fastx_file(&path)? -> Err
+        fx = read_fastx(paths[i], /*io_error_on_open=*/true);  // parse_fastx_file(&path)? -> Err
       } catch (const Panic &e) {
         throw IoError(e.what());  // count() propagates parse errors with `?`
       }
       size_t bases = 0;
+      const std::vector<Record> &recs = fx.recs;
       for (const Record &r : recs) bases += r.seq.size();
       if (i) js += ',';
       js += "{\"path\":\"";

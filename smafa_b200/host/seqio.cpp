@@ -3,6 +3,7 @@
 #include <zlib.h>
 
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -88,7 +89,7 @@ void encode_or_panic(const Record &r, uint64_t *out, int alphabet) {
   size_t bad = 0;
   if (!encode_window(reinterpret_cast<const uint8_t *>(r.seq.data()), r.seq.size(), out, &bad, alphabet))
     throw Panic("Byte " + std::to_string((unsigned)(uint8_t)r.seq[bad]) + " cannot be interpreted as " +
-                (alphabet ? "amino acid" : "nucleotide") + ", in sequence \"" + r.id + "\" at position " +
+                (alphabet ? "amino acid" : "nucleotide") + ", in sequence \"" + std::string(r.id) + "\" at position " +
                 std::to_string(bad));
 }
 
@@ -131,17 +132,35 @@ void parallel_chunks(size_t n, size_t min_per_thread, const std::function<void(u
     if (e) std::rethrow_exception(e);  // the lowest-numbered chunk's failure, i.e. the first in input order
 }
 
-std::vector<uint8_t> read_file(const std::string &path) {
+Bytes read_file(const std::string &path) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f)
     throw IoError("Os { code: " + std::to_string(errno) + ", kind: NotFound, message: \"" + strerror(errno) + "\" }");
-  std::vector<uint8_t> buf;
+  Bytes buf;
   struct stat st;
-  if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {  // one allocation, one read
+  if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {  // one allocation
     buf.resize((size_t)st.st_size);
-    size_t got = 0, r;
-    while (got < buf.size() && (r = fread(buf.data() + got, 1, buf.size() - got, f)) > 0) got += r;
-    buf.resize(got);
+    const size_t n = buf.size();
+    const int fd = fileno(f);
+    std::atomic<bool> short_read{false};
+    // large files: every host thread preads its own range (the page faults of the fresh buffer and the copy out of
+    // the page cache are the cost, and both parallelise)
+    parallel_chunks(n, 32u << 20, [&](unsigned, size_t lo, size_t hi) {
+      size_t got = lo;
+      while (got < hi) {
+        const ssize_t r = pread(fd, buf.data() + got, hi - got, (off_t)got);
+        if (r <= 0) { short_read = true; return; }
+        got += (size_t)r;
+      }
+    });
+    if (short_read) {  // the file shrank under us, or an I/O error: fall back to one sequential read
+      size_t got = 0, r;
+      rewind(f);
+      while (got < n && (r = fread(buf.data() + got, 1, n - got, f)) > 0) got += r;
+      buf.resize(got);
+    } else {
+      fseek(f, (long)n, SEEK_SET);
+    }
   }
   uint8_t tmp[1 << 16];  // pipes, or a file that grew
   size_t r;
@@ -150,7 +169,7 @@ std::vector<uint8_t> read_file(const std::string &path) {
   return buf;
 }
 
-static std::vector<uint8_t> read_maybe_gz(const std::string &path, bool io_error_on_open) {
+static Bytes read_maybe_gz(const std::string &path, bool io_error_on_open) {
   FILE *probe = fopen(path.c_str(), "rb");
   if (!probe) {
     std::string msg = "Os { code: " + std::to_string(errno) + ", kind: NotFound, message: \"" + strerror(errno) + "\" }";
@@ -164,7 +183,7 @@ static std::vector<uint8_t> read_maybe_gz(const std::string &path, bool io_error
   gzFile g = gzopen(path.c_str(), "rb");
   if (!g) throw IoError("cannot open " + path);
   gzbuffer(g, 1 << 20);
-  std::vector<uint8_t> buf;
+  Bytes buf;
   std::vector<uint8_t> tmp(1 << 20);
   for (;;) {
     int r = gzread(g, tmp.data(), (unsigned)tmp.size());
@@ -194,70 +213,80 @@ static void append_stripped(std::string &dst, const uint8_t *b, size_t n) {
   }
 }
 
-std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open) {
-  const std::vector<uint8_t> buf = read_maybe_gz(path, io_error_on_open);
-  const uint8_t *b = buf.data();
-  const size_t n = buf.size();
-  std::vector<Record> out;
+FastxFile read_fastx(const std::string &path, bool io_error_on_open) {
+  FastxFile f;
+  f.buf = read_maybe_gz(path, io_error_on_open);
+  const uint8_t *b = f.buf.data();
+  const size_t n = f.buf.size();
   if (n == 0) throw Panic("valid path/file: EmptyFile");
-  size_t p = 0;
+  auto view = [&](size_t lo, size_t hi) { return std::string_view(reinterpret_cast<const char *>(b + lo), hi - lo); };
   if (b[0] == '>') {
-    // Records of [lo, hi): lo is a record start ('>' at the start of a line), hi is the next chunk's start.
-    auto parse_range = [&](size_t lo, size_t hi, std::vector<Record> &dst) {
-      size_t p = lo;
-      while (p < hi) {
-        if (b[p] != '>') throw Panic("valid record: InvalidStart");
-        size_t he = p + 1;
-        const void *nl = memchr(b + he, '\n', n - he);
-        he = nl ? (size_t)((const uint8_t *)nl - b) : n;
-        size_t idn = he - (p + 1);
-        if (idn && b[p + idn] == '\r') --idn;
-        Record r;
-        r.id.assign(reinterpret_cast<const char *>(b + p + 1), idn);
-        size_t ss = he < n ? he + 1 : n, se = ss;
-        while (se < n) {  // next '>' at the start of a line ends the record
-          const void *gt = memchr(b + se, '>', n - se);
-          if (!gt) { se = n; break; }
-          se = (const uint8_t *)gt - b;
-          if (se == ss || b[se - 1] == '\n') break;
-          ++se;
-        }
-        r.seq.reserve(se - ss);
-        append_stripped(r.seq, b + ss, se - ss);
-        dst.push_back(std::move(r));
-        p = se;
+    // the next record start ('>' at the start of a line) at or after q
+    auto next_start = [&](size_t q) {
+      while (q < n) {
+        const void *gt = memchr(b + q, '>', n - q);
+        if (!gt) return n;
+        q = (size_t)((const uint8_t *)gt - b);
+        if (q == 0 || b[q - 1] == '\n') return q;
+        ++q;
       }
+      return n;
     };
     // chunk boundaries = the first record start at or after the nominal split points
     const unsigned T = n >= (8u << 20) ? host_threads() : 1;
     std::vector<size_t> cut(T + 1, n);
     cut[0] = 0;
-    for (unsigned t = 1; t < T; ++t) {
-      size_t q = std::max(cut[t - 1], n * t / T);
-      while (q < n) {
-        const void *gt = memchr(b + q, '>', n - q);
-        if (!gt) { q = n; break; }
-        q = (const uint8_t *)gt - b;
-        if (q == 0 || b[q - 1] == '\n') break;
-        ++q;
+    for (unsigned t = 1; t < T; ++t) cut[t] = next_start(std::max(cut[t - 1], n * t / T));
+    // pass 1: records per chunk, so that pass 2 can write them in place (no per-thread lists to merge)
+    std::vector<size_t> first(T + 1, 0);
+    parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+      for (size_t t = t0; t < t1; ++t) {
+        size_t cnt = 0;
+        for (size_t p = cut[t]; p < cut[t + 1]; p = next_start(p + 1)) {
+          if (b[p] != '>') throw Panic("valid record: InvalidStart");
+          ++cnt;
+        }
+        first[t + 1] = cnt;
       }
-      cut[t] = q;
-    }
-    if (T == 1) {
-      parse_range(0, n, out);
-    } else {
-      std::vector<std::vector<Record>> parts(T);
-      parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
-        for (size_t t = t0; t < t1; ++t) parse_range(cut[t], cut[t + 1], parts[t]);
-      });
-      size_t total = 0;
-      for (auto &v : parts) total += v.size();
-      out.reserve(total);
-      for (auto &v : parts)
-        for (auto &r : v) out.push_back(std::move(r));
-    }
-    p = n;
+    });
+    for (unsigned t = 0; t < T; ++t) first[t + 1] += first[t];
+    f.recs.resize(first[T]);
+    f.arenas.resize(T);
+    // pass 2: records of [cut[t], cut[t+1])
+    parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
+      for (size_t t = t0; t < t1; ++t) {
+        Record *dst = f.recs.data() + first[t];
+        size_t p = cut[t];
+        const size_t hi = cut[t + 1];
+        while (p < hi) {
+          size_t he = p + 1;
+          const void *nl = memchr(b + he, '\n', n - he);
+          he = nl ? (size_t)((const uint8_t *)nl - b) : n;
+          size_t idn = he - (p + 1);
+          if (idn && b[p + idn] == '\r') --idn;
+          Record r;
+          r.id = view(p + 1, p + 1 + idn);
+          const size_t ss = he < n ? he + 1 : n, se = next_start(ss);
+          // the usual record is one sequence line: a view into the file, trailing line end excluded
+          size_t le = se;
+          if (le > ss && b[le - 1] == '\n') --le;
+          while (le > ss && b[le - 1] == '\r') --le;
+          if (memchr(b + ss, '\n', le - ss) == nullptr && memchr(b + ss, '\r', le - ss) == nullptr) {
+            r.seq = view(ss, le);
+          } else {
+            std::string joined;
+            joined.reserve(se - ss);
+            append_stripped(joined, b + ss, se - ss);
+            f.arenas[t].push_back(std::move(joined));
+            r.seq = f.arenas[t].back();
+          }
+          *dst++ = r;
+          p = se;
+        }
+      }
+    });
   } else if (b[0] == '@') {
+    size_t p = 0;
     while (p < n) {
       if (b[p] == '\n' || b[p] == '\r') { ++p; continue; }
       if (b[p] != '@') throw Panic("valid record: InvalidStart");
@@ -270,52 +299,59 @@ std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open) {
         if (le[l] > ls[l] && b[le[l] - 1] == '\r') --le[l];
         if (p < n) ++p;
       }
-      Record r;
-      r.id.assign(reinterpret_cast<const char *>(b + ls[0] + 1), le[0] - ls[0] - 1);
-      r.seq.assign(reinterpret_cast<const char *>(b + ls[1]), le[1] - ls[1]);
-      out.push_back(std::move(r));
+      f.recs.push_back(Record{view(ls[0] + 1, le[0]), view(ls[1], le[1])});
     }
   } else {
     throw Panic("valid path/file: InvalidStart");
   }
-  return out;
+  return f;
 }
 
 // ---- db bytes: varint(version) varint(n) n x [varint(W) W x varint(u64)] option(len) ----
 
-static inline void put_varint(std::vector<uint8_t> &o, uint64_t v) {
+static inline void put_varint(Bytes &o, uint64_t v) {
   while (v >= 0x80) { o.push_back((uint8_t)(v | 0x80)); v >>= 7; }
   o.push_back((uint8_t)v);
 }
 
-std::vector<uint8_t> serialize_db(const WindowDb &db) {
-  // windows are encoded on all host threads into per-chunk buffers and concatenated in order
+static inline size_t varint_len(uint64_t v) { return (size_t)(70 - __builtin_clzll(v | 1)) / 7; }
+static inline uint8_t *put_varint_raw(uint8_t *o, uint64_t v) {
+  while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
+  *o++ = (uint8_t)v;
+  return o;
+}
+
+Bytes serialize_db(const WindowDb &db) {
+  // Two passes on all host threads: the encoded size of every chunk of windows, then each chunk written in place
+  // at its offset (no per-chunk buffers to concatenate, no capacity check per byte).
   const unsigned T = db.n >= 65536 ? host_threads() : 1;
-  std::vector<std::vector<uint8_t>> parts(T);
+  std::vector<size_t> off(T + 1, 0);
+  const size_t wlen = varint_len(db.W);
   parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
     for (size_t t = t0; t < t1; ++t) {
       const uint64_t lo = db.n * t / T, hi = db.n * (t + 1) / T;
-      std::vector<uint8_t> &o = parts[t];
-      o.reserve((hi - lo) * (1 + 9 * (size_t)db.W));
-      for (uint64_t i = lo; i < hi; ++i) {
-        put_varint(o, db.W);
-        for (uint32_t w = 0; w < db.W; ++w) put_varint(o, db.words[i * db.W + w]);
-      }
+      size_t bytes = (size_t)(hi - lo) * wlen;
+      const uint64_t *w = db.words.data() + lo * db.W, *e = db.words.data() + hi * db.W;
+      for (; w < e; ++w) bytes += varint_len(*w);
+      off[t + 1] = bytes;
     }
   });
-  size_t body = 0;
-  for (const auto &v : parts) body += v.size();
-  std::vector<uint8_t> o;
-  o.reserve(32 + body);
+  Bytes o;
   put_varint(o, DB_VERSION);
   put_varint(o, db.n);
   const size_t head = o.size();
-  o.resize(head + body);
-  std::vector<size_t> off(T + 1, head);
-  for (unsigned t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+  off[0] = head;
+  for (unsigned t = 0; t < T; ++t) off[t + 1] += off[t];
+  o.resize(off[T]);
   parallel_chunks(T, 1, [&](unsigned, size_t t0, size_t t1) {
-    for (size_t t = t0; t < t1; ++t)
-      if (!parts[t].empty()) memcpy(o.data() + off[t], parts[t].data(), parts[t].size());
+    for (size_t t = t0; t < t1; ++t) {
+      const uint64_t lo = db.n * t / T, hi = db.n * (t + 1) / T;
+      uint8_t *p = o.data() + off[t];
+      for (uint64_t i = lo; i < hi; ++i) {
+        p = put_varint_raw(p, db.W);
+        for (uint32_t w = 0; w < db.W; ++w) p = put_varint_raw(p, db.words[i * db.W + w]);
+      }
+    }
   });
   if (db.L) { o.push_back(1); put_varint(o, db.L); }
   else o.push_back(0);
@@ -430,7 +466,7 @@ static bool parse_body_parallel(Cursor &c, WindowDb &db) {
   return true;
 }
 
-WindowDb parse_db(const std::vector<uint8_t> &bytes) {
+WindowDb parse_db(const Bytes &bytes) {
   if (bytes.size() < 4)  // &buffer[0..4], src/lib.rs:214
     throw Panic("range end index 4 out of range for slice of length " + std::to_string(bytes.size()));
   Cursor head{bytes.data(), 4};

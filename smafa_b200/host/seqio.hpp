@@ -3,9 +3,12 @@
 // decode helpers of the reference (src/lib.rs:29-52,113-135,137-165,167-196,206-218).
 #pragma once
 #include <cstdint>
+#include <deque>
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <vector>
 
 namespace smafa_host {
@@ -27,14 +30,38 @@ void parallel_chunks(size_t n, size_t min_per_thread, const std::function<void(u
 
 constexpr uint32_t DB_VERSION = 2;  // CURRENT_DB_VERSION, src/lib.rs:18
 
+// File contents: a byte vector whose resize() does not zero-fill (a whole-file read would otherwise touch every page
+// twice), read with parallel pread()s when the file is large.
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using Bytes = std::vector<uint8_t, DefaultInitAlloc<uint8_t>>;
+using Words = std::vector<uint64_t, DefaultInitAlloc<uint64_t>>;  // every element is written by the (parallel) decoder / encoder
+
+// One FASTX record as views into its FastxFile (no per-record allocation: 10 M records used to cost 20 M mallocs and
+// a gigabyte of freshly faulted pages, which bounded the "multi-threaded" parse at one thread's speed).
 struct Record {
-  std::string id;   // header line without '>' / '@'
-  std::string seq;  // line endings stripped, case preserved
+  std::string_view id;   // header line without '>' / '@'
+  std::string_view seq;  // line endings stripped, case preserved
+};
+struct FastxFile {
+  Bytes buf;                                      // the (decompressed) file: single-line sequences are views into it
+  std::vector<std::deque<std::string>> arenas;    // re-assembled sequences (multi-line, stray CR), one arena per parser thread
+  std::vector<Record> recs;
+  FastxFile() = default;
+  FastxFile(FastxFile &&) = default;              // moving keeps every heap block, so the views stay valid
+  FastxFile &operator=(FastxFile &&) = default;
+  FastxFile(const FastxFile &) = delete;
+  FastxFile &operator=(const FastxFile &) = delete;
 };
 
 // Whole-file FASTX parse (plain or gzip, sniffed by zlib).  Throws Panic on malformed input
 // (the reference .expect()s needletail's result) and IoError when the file cannot be opened.
-std::vector<Record> read_fastx(const std::string &path, bool io_error_on_open = false);
+FastxFile read_fastx(const std::string &path, bool io_error_on_open = false);
 
 extern const uint8_t SYMBOL_CODE[256];  // src/lib.rs:167-184; 0 = not a nucleotide
 // Protein extension (not in the reference): symbol numbers 1..20 = ACDEFGHIKLMNPQRSTVWY,
@@ -48,14 +75,14 @@ void encode_or_panic(const Record &r, uint64_t *out, int alphabet = 0);  // pani
 void decode_window(const uint64_t *words, size_t len, char *out, int alphabet = 0);  // src/lib.rs:113-135
 
 struct WindowDb {
-  std::vector<uint64_t> words;  // [n][W]
+  Words words;  // [n][W]
   uint64_t n = 0;
   uint32_t W = 0;
   uint32_t L = 0;  // 0 == None (empty db)
 };
 
-std::vector<uint8_t> serialize_db(const WindowDb &db);  // == postcard::to_allocvec(&WindowSet)
-WindowDb parse_db(const std::vector<uint8_t> &bytes);   // version gate of src/lib.rs:212-217
-std::vector<uint8_t> read_file(const std::string &path);
+Bytes serialize_db(const WindowDb &db);  // == postcard::to_allocvec(&WindowSet)
+WindowDb parse_db(const Bytes &bytes);                  // version gate of src/lib.rs:212-217
+Bytes read_file(const std::string &path);
 
 }  // namespace smafa_host
