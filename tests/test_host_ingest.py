@@ -110,3 +110,52 @@ def test_cluster_deduplication_matches_numpy_for_every_thread_count():
         r = subprocess.run([sys.executable, "-c", DEDUP], env=env, capture_output=True, text=True, check=True)
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0].startswith("OK") and len(set(outs)) == 1, outs
+
+
+def _py_encode(seqs, L):
+    """Reference word layout (src/lib.rs:29-52) of already-clean sequences, for the format tests below."""
+    code = {**{c: 16 for c in "Aa"}, **{c: 8 for c in "Cc"}, **{c: 4 for c in "Gg"}, **{c: 2 for c in "TtUu"}}
+    W = (L + 11) // 12
+    out = np.zeros((len(seqs), W), dtype=np.uint64)
+    for i, s in enumerate(seqs):
+        assert len(s) == L
+        for p, ch in enumerate(s):
+            out[i, p // 12] |= np.uint64(code.get(ch, 1)) << np.uint64(5 * (p % 12))
+    return out
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_fasta_layout_variants_parse_alike(tmp_path, threads):
+    """Line structure must not change what is encoded: multi-line sequences, CRLF line ends, blank lines, '>' inside a
+    header, lower case, no newline at the end of the file.  Only the single-line / no-trailing-newline shapes are pinned
+    by reference fixtures (tests/data/subjects.fa); the others follow needletail's documented behaviour
+    and are checked against the oracle CLI and a Python model of the encoding."""
+    rng = np.random.default_rng(3)
+    L, n = 60, 9000
+    seqs = ["".join(rng.choice(list("ACGTNacgt-RY"), size=L)) for _ in range(n)]
+    want = _py_encode(seqs, L)
+    variants = {
+        "plain": "".join(f">s{i} d>x\n{s}\n" for i, s in enumerate(seqs)),
+        "no_final_newline": "".join(f">s{i}\n{s}\n" for i, s in enumerate(seqs))[:-1],
+        "multiline": "".join(f">s{i}\n{s[:17]}\n{s[17:40]}\n{s[40:]}\n" for i, s in enumerate(seqs)),
+        "crlf": "".join(f">s{i}\r\n{s}\r\n" for i, s in enumerate(seqs)),
+        "crlf_multiline": "".join(f">s{i}\r\n{s[:30]}\r\n{s[30:]}\r\n" for i, s in enumerate(seqs)),
+        "blank_lines": "".join(f">s{i}\n{s}\n\n" for i, s in enumerate(seqs)),
+    }
+    env = dict(os.environ, SMAFA_HOST_THREADS=str(threads))
+    from oracle import c_oracle
+    c_oracle.build()
+    for name, text in variants.items():
+        fa = tmp_path / f"{name}.fna"
+        reps = 1 if threads == 1 else 20  # > 8 MB: the multi-threaded parse
+        sep = "\n" if name == "no_final_newline" else ""
+        fa.write_bytes(sep.join([text] * reps).encode())
+        r = subprocess.run([api.CLI_PATH, "makedb", "-i", fa, "-d", tmp_path / f"{name}.db"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.stderr)
+        w, got_L = api.load_db_file(str(tmp_path / f"{name}.db"))
+        assert got_L == L and w.shape == (n * reps, 5), name
+        assert (w.reshape(reps, n, 5) == want[None]).all(), name
+        if threads == 1 and name in ("plain", "no_final_newline", "multiline", "crlf"):
+            o = subprocess.run([c_oracle.CLI, "makedb", "-i", fa, "-d", tmp_path / f"{name}.odb"], capture_output=True, text=True)
+            assert o.returncode == 0, (name, o.stderr)
+            assert (tmp_path / f"{name}.odb").read_bytes() == (tmp_path / f"{name}.db").read_bytes(), name
