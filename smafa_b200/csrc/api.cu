@@ -68,8 +68,18 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   smafa_ctx *ctx = nullptr;
   if (!out) return fail(nullptr, SMAFA_E_INVALID, "smafa_ctx_create: null out pointer");
   *out = nullptr;
+  // SMAFA_TIMING=1: where context creation spends its 1-3 s (stderr)
+  const bool timing = getenv("SMAFA_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[smafa timing] ctx: %-23s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
+  lap("cudaGetDeviceCount");
   if (e != cudaSuccess || n == 0)
     return fail(nullptr, SMAFA_E_CUDA,
                 "no CUDA device available (%s); libsmafa_b200 has no CPU fallback",
@@ -80,7 +90,10 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   if (prop.major != 10)
     return fail(nullptr, SMAFA_E_CUDA, "device %d is sm_%d%d; libsmafa_b200 holds sm_100a code only", device,
                 prop.major, prop.minor);
+  lap("cudaGetDeviceProperties");
   CU(cudaSetDevice(device));
+  CU(cudaFree(nullptr));  // forces the primary context into existence here
+  lap("primary context");
   ctx = new smafa_ctx();
   ctx->device = device;
   ctx->kernel = kernel;
@@ -94,6 +107,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
   cudaHostAlloc((void **)&ctx->h_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long), cudaHostAllocDefault);
   cudaMalloc((void **)&ctx->d_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long));
+  lap("stream, events, scalars");
   *out = ctx;
   return SMAFA_OK;
 }
