@@ -59,8 +59,12 @@ def parse_args():
     ap.add_argument("--max-divergence", default=None, help="integer or 'none' (default 5 = configs[1]; protein: none)")
     ap.add_argument("--alphabet", default="nucleotide", choices=["nucleotide", "protein"],
                     help="protein = the configs[3] shape (20-aa windows, --max-num-hits 10), an extension without reference parity")
+    ap.add_argument("--window-length", type=int, default=None,
+                    help="ablation only: nucleotide windows of another length (the headline workload is 60 nt)")
     a = ap.parse_args()
     global L
+    if a.window_length and a.alphabet == "nucleotide":
+        L = a.window_length
     if a.alphabet == "protein":
         L, a.mode = 20, "b"
         a.max_divergence = a.max_divergence or "none"

@@ -222,6 +222,15 @@ int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_e
 /* Measured dense int8 tcgen05 rate of this GPU in TOP/s (roofline denominator of the MMA kernel):
  * every SM issues mmas_per_cta back-to-back M128 x N256 x K32 kind::i8 MMAs on resident operands. */
 int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops);
+/* Issue rate of other instruction shapes a scan could use, in ns per k-step and SM (csrc/probe.cu):
+ * shape 0 = dense M128 x N256 x K32 (the shape the scan issues), 1 = the same k-step as two N = 128 instructions,
+ * 2 = 2:4-sparse kind::i8 M128 x N256 x K64 (tcgen05.mma.sp; a one-hot window operand is a legal sparse A). */
+int smafa_debug_mma_rate(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step);
+/* What the tensor core reconstructs from (compressed A, sparsity metadata): out[s][m][k] = logical A element k of
+ * row m in step s (B is the identity).  a_comp [128][64] int8 (32 per step), meta [128][4] u32 (2 per step),
+ * n_steps 1 or 2, meta_path 0 = tcgen05.st, 1 = tcgen05.cp.128x128b from 16-byte shared-memory rows. */
+int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path,
+                              int32_t *out /* [n_steps][128][64] */);
 /* Contraction depth K (int8 elements per window) of the tcgen05 operands of this db, 0 if the db is
  * not eligible for the MMA kernel: executed int8 ops per comparison = 2 * K. */
 uint32_t smafa_db_mma_k(const smafa_db *db);

@@ -97,6 +97,8 @@ def load_library():
     l.smafa_db_file_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
     l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
     l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
+    l.smafa_debug_mma_rate.argtypes = [vp, C.c_int, u32, C.POINTER(C.c_double)]
+    l.smafa_debug_sparse_decode.argtypes = [vp, vp, vp, u32, C.c_int, vp]
     l.smafa_db_mma_k.restype = u32
     l.smafa_db_mma_k.argtypes = [vp]
     l.smafa_encode_symbol.restype = C.c_uint8
@@ -241,6 +243,24 @@ class Context:
         if rc:
             _raise(rc, self._h)
         return t.value
+
+    def mma_rate_ns(self, shape, n_steps=40000):
+        """ns per k-step and SM for instruction shape 0 (dense N256), 1 (2 x N128), 2 (sparse K64); see smafa_b200.h."""
+        t = C.c_double(0)
+        rc = self._l.smafa_debug_mma_rate(self._h, int(shape), int(n_steps), C.byref(t))
+        if rc:
+            _raise(rc, self._h)
+        return t.value
+
+    def debug_sparse_decode(self, a_comp, meta, n_steps=2, meta_path=0):
+        """Logical A rows the tensor core reconstructs from compressed values + metadata: int32 [n_steps, 128, 64]."""
+        a = np.ascontiguousarray(a_comp, dtype=np.int8).reshape(128, 64)
+        m = np.ascontiguousarray(meta, dtype=np.uint32).reshape(128, 4)
+        out = np.zeros((n_steps, 128, 64), dtype=np.int32)
+        rc = self._l.smafa_debug_sparse_decode(self._h, a.ctypes.data, m.ctypes.data, int(n_steps), int(meta_path), out.ctypes.data)
+        if rc:
+            _raise(rc, self._h)
+        return out
 
     def debug_mma_dump(self, db, q_enc, bound):
         """Raw tcgen05 accumulators of the first db tile: int32 [128, 256] (see smafa_b200.h)."""

@@ -939,3 +939,17 @@ extern "C" int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, doubl
   *tops = 2.0 * 128 * 256 * 32 * (double)mmas_per_cta * ctx->num_sms / (ms * 1e-3) / 1e12;
   return SMAFA_OK;
 }
+
+extern "C" int smafa_debug_mma_rate(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step) {
+  if (!ctx || !ns_per_step || n_steps == 0 || shape < 0 || shape > 2) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_rate: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  return mma_rate_probe(ctx, shape, n_steps, ns_per_step);
+}
+
+extern "C" int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path,
+                                         int32_t *out) {
+  if (!ctx || !a_comp || !meta || !out || n_steps < 1 || n_steps > 2 || meta_path < 0 || meta_path > 1)
+    return fail(ctx, SMAFA_E_INVALID, "smafa_debug_sparse_decode: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  return sparse_decode_probe(ctx, a_comp, meta, n_steps, meta_path, out);
+}

@@ -80,3 +80,6 @@ void mma_db_free(smafa_db *db);
 // returns kernels launched (>= 0) or a negative smafa_status
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s, int32_t *dump = nullptr);
 int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms);
+// probe.cu
+int mma_rate_probe(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step);
+int sparse_decode_probe(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path, int32_t *out);

@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "tcgen05.cuh"
 
 namespace smafa {
 
@@ -88,111 +89,6 @@ __host__ __device__ __forceinline__ uint32_t had_spare_k(uint32_t si, uint32_t P
   return (si / gap) * PB + L + si % gap;
 }
 __host__ __device__ __forceinline__ int clamp8(int v) { return v < -128 ? -128 : (v > 127 ? 127 : v); }
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// One elected lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on a
-// single thread and emits tcgen05.mma / bulk copies directly instead of a per-active-lane loop.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-template <bool ACCUMULATE>
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACCUMULATE ? 1 : 0), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-// Same shape with .pack::16b: register i = low 16 bits of column 2i | low 16 bits of column 2i+1 << 16, i.e.
-// 64 accumulator columns per load.  |D| < 2^15 for every encoding, so bit 15 is still the sign.
-__device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_NONE [61,64).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
-         (1ull << 46);
-}
-
-// Byte offset of element (row, kbyte) inside a tile image: 8-row groups of KB*8 bytes, inside a
-// group the 16-byte k-chunks are 128 bytes apart and the 8 rows of a chunk are contiguous.
-__host__ __device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t kbyte, uint32_t KB) {
-  return (row >> 3) * (8 * KB) + (kbyte >> 4) * 128 + (row & 7) * 16 + (kbyte & 15);
-}
 
 // Survivors of the sign filter are not verified by the warp that finds them: verification is a chain of
 // dependent L2 round trips (reference words, bound, candidate slot, histogram), and with only two accumulator
@@ -262,7 +158,12 @@ __device__ __forceinline__ AndTree and_tree32(const uint32_t (&v)[32]) {
 //           the query's N count nN_q, the bias uses need_q - nN_q and the filter stays conservative:
 //           matches >= need  =>  base matches >= need - nN_q  =>  D >= 0.  Survivors are verified exactly.
 // B_BUFS = 2: the query operand of the next work item is fetched while the current item computes.
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS>
+// SPLIT_N: every k-step is issued as two M128xN128 instructions, query half h into accumulator columns
+//          [128h, 128h+128) of the buffer, and each half has its own full/empty barrier pair: the epilogue warps of
+//          half 0 drain while the MMAs of half 1 run, and an accumulator half is refilled as soon as ITS four warps
+//          have read it (four half-buffers in flight instead of two whole ones).  Same tensor cycles per tile
+//          (128*N/256 per instruction), finer hand-over.
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS, bool SPLIT_N>
 __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
@@ -282,19 +183,21 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
-  static_assert(2 * STAGES + 10 <= 24, "barrier block holds 24 mbarriers");
+  static_assert(2 * STAGES + 14 <= 24, "barrier block holds 24 mbarriers");
+  static_assert(!SPLIT_N || EPI_WARPS == 8, "SPLIT_N: one epilogue warp per (lane quarter, accumulator half)");
+  constexpr uint32_t ACC_UNITS = SPLIT_N ? 4 : 2;  // accumulator hand-over units: (buffer, half) or whole buffers
   auto FULL = [&](uint32_t s) { return bar0 + 8 * s; };
   auto EMPTY = [&](uint32_t s) { return bar0 + 8 * (STAGES + s); };
-  auto TFULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + b); };
-  auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
-  auto B_FULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 4 + b); };
-  auto B_EMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 6 + b); };
-  auto B_READY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 8 + b); };
+  auto TFULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + b); };        // b = buffer, or 2*buffer + half
+  auto TEMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 4 + b); };
+  auto B_FULL = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 8 + b); };
+  auto B_EMPTY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 10 + b); };
+  auto B_READY = [&](uint32_t b) { return bar0 + 8 * (2 * STAGES + 12 + b); };
 
   if (threadIdx.x < 48) ring_ctl[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (uint32_t b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS); }
+    for (uint32_t b = 0; b < ACC_UNITS; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), MMA_EPI_WARPS * 2 / ACC_UNITS); }
     for (uint32_t b = 0; b < 2; ++b) { mbar_init(B_FULL(b), 1); mbar_init(B_EMPTY(b), 1); mbar_init(B_READY(b), 1); }
     fence_barrier_init();
   }
@@ -401,7 +304,8 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
     // ===== MMA issuer =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32 [4,6)=2, A=S8 [7,10)=1, B=S8 [10,13)=1,
     // K-major A/B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+    constexpr uint32_t N_INST = SPLIT_N ? MMA_N / 2 : MMA_N;
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_INST >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
     uint32_t stage = 0, phase = 0, tcount = 0, item_count = 0;
     // descriptors: only the 14-bit start-address field changes (stage and k-step offsets, in 16-byte units)
     const uint64_t desc_hi = ((uint64_t)(P.desc_lbo & 0x3FFFu) << 16) | ((uint64_t)(P.desc_sbo & 0x3FFFu) << 32) | (1ull << 46);
@@ -415,21 +319,42 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
       mbar_wait(B_READY(bb_), (item_count / B_BUFS) & 1);
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
-        mbar_wait(TEMPTY(buf), (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
-        mbar_wait(FULL(stage), phase);          // A tile has landed
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + buf * MMA_N;
+        if constexpr (SPLIT_N) {
+          mbar_wait(FULL(stage), phase);  // A tile has landed
           const uint64_t ad = adesc_base + (uint64_t)(stage * (A_BYTES >> 4));
-          tc_mma_i8<false>(d_tmem, ad, bdesc_base, idesc);
 #pragma unroll
-          for (uint32_t ks = 1; ks < (uint32_t)KSTEPS; ++ks)
-            tc_mma_i8<true>(d_tmem, ad + ks * 16, bdesc_base + ks * 16, idesc);  // +256 bytes per k-step
-          tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
-          tc_commit(TFULL(buf));    // accumulator ready for the epilogue
-          if (t + 1 == t_end) tc_commit(B_EMPTY(bb_));
+          for (uint32_t h = 0; h < 2; ++h) {
+            mbar_wait(TEMPTY(2 * buf + h), (use & 1) ^ 1);  // the four warps of this half have read it
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + buf * MMA_N + h * N_INST;
+              const uint64_t bd = bdesc_base + (uint64_t)(h * (N_INST * KB >> 4));  // query rows 128h.. of the tile image
+              tc_mma_i8<false>(d_tmem, ad, bd, idesc);
+#pragma unroll
+              for (uint32_t ks = 1; ks < (uint32_t)KSTEPS; ++ks) tc_mma_i8<true>(d_tmem, ad + ks * 16, bd + ks * 16, idesc);
+              if (h == 1) tc_commit(EMPTY(stage));
+              tc_commit(TFULL(2 * buf + h));
+              if (h == 1 && t + 1 == t_end) tc_commit(B_EMPTY(bb_));
+            }
+            __syncwarp();
+          }
+        } else {
+          mbar_wait(TEMPTY(buf), (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+          mbar_wait(FULL(stage), phase);          // A tile has landed
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + buf * MMA_N;
+            const uint64_t ad = adesc_base + (uint64_t)(stage * (A_BYTES >> 4));
+            tc_mma_i8<false>(d_tmem, ad, bdesc_base, idesc);
+#pragma unroll
+            for (uint32_t ks = 1; ks < (uint32_t)KSTEPS; ++ks)
+              tc_mma_i8<true>(d_tmem, ad + ks * 16, bdesc_base + ks * 16, idesc);  // +256 bytes per k-step
+            tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
+            tc_commit(TFULL(buf));    // accumulator ready for the epilogue
+            if (t + 1 == t_end) tc_commit(B_EMPTY(bb_));
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -530,7 +455,8 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
       const uint32_t qbase = qt * MMA_N + part * COLS_PER_WARP;
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
-        mbar_wait(TFULL(buf), use & 1);
+        const uint32_t unit = SPLIT_N ? 2 * buf + part : buf;  // the barrier pair this warp hands over on
+        mbar_wait(TFULL(unit), use & 1);
         tc_fence_after();
         const uint32_t row = t * MMA_M + quarter * 32 + lane;
         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N + part * COLS_PER_WARP;
@@ -568,7 +494,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
           tc_wait_ld();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(TEMPTY(buf));
+          if (lane == 0) mbar_arrive(TEMPTY(unit));
           process(va, 0);
         } else {
           // two loads in flight; the buffer is released after the last wait
@@ -581,7 +507,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
             if (c + 2 == CHUNKS) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(TEMPTY(buf));
+              if (lane == 0) mbar_arrive(TEMPTY(unit));
             }
             process(va, c);
             if (c + 2 < CHUNKS) load(c + 2, va);
@@ -878,12 +804,12 @@ void mma_db_free(smafa_db *db) {
   db->onehot_cap = 0;
 }
 
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2>
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2, bool SPLIT_N = false>
 static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
   constexpr size_t smem = (size_t)B_BUFS * MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 512 +
                           (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
   static_assert(smem <= 232448, "more than 227 KB of shared memory");
-  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS>;
+  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS, SPLIT_N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mma_threads(EPI_WARPS), smem, s>>>(P);
@@ -938,6 +864,15 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   // shape measured there is gone since the verifier warps took its register budget); SMAFA_MMA_PACK16=0 keeps the
   // unpacked loads of the default encoding reachable.
   static const bool pack16 = getenv("SMAFA_MMA_PACK16") ? atoi(getenv("SMAFA_MMA_PACK16")) != 0 : true;
+  // SMAFA_MMA_SPLIT_N=1: two N = 128 instructions per k-step with per-half accumulator hand-over (see the kernel)
+  static const bool split_n = getenv("SMAFA_MMA_SPLIT_N") ? atoi(getenv("SMAFA_MMA_SPLIT_N")) != 0 : false;
+  if (split_n && pack16 && (db->mma_nsym == 2 || db->mma_nsym == 3 || (db->mma_nsym == 4 && wide))) {
+    if (db->mma_nsym == 4) e = launch_mma<8, 4, 2, 8, true, 2, true>(P, grid, s);
+    else if (db->mma_nsym == 2) e = wide ? launch_mma<4, 2, 4, 8, true, 2, true>(P, grid, s) : launch_mma<2, 2, 4, 8, true, 2, true>(P, grid, s);
+    else e = wide ? launch_mma<6, 3, 4, 8, true, 2, true>(P, grid, s) : launch_mma<3, 3, 4, 8, true, 2, true>(P, grid, s);
+    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
+    return 2;
+  }
   switch (db->mma_nsym) {
     case MMA_ENC_AA: e = launch_mma<13, (int)MMA_ENC_AA, 2, 8, true, 1>(P, grid, s); break;
     case 5: e = wide ? launch_mma<10, 5, 3, 8, true, 1>(P, grid, s) : launch_mma<5, 5, 4, 8, true>(P, grid, s); break;
