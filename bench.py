@@ -188,9 +188,10 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
     secs = scan_ms / 1e3
     if kernel_used == 2:
         # Algorithmic work: one-hot(query) . one-hot(db)^T over 5 symbols x L = 2*5*L int8 ops per
-        # comparison.  The kernel contracts over a denser operand encoding (+-1 character features of the 2-bit
-        # base code, K = mma_k per window), so it EXECUTES 2*mma_k ops per comparison: `frac` (algorithmic, the
-        # contract's definition) can exceed 1; `frac_executed` is the tensor-pipe utilisation.
+        # comparison.  The kernel contracts over denser operands (+-1 character features of the 2-bit base code,
+        # K = 192 per window; or one-hot union rows, two windows per accumulator, K = 128 per window), so it
+        # EXECUTES 2*mma_k ops per comparison: `frac` (algorithmic, the contract's definition) can exceed 1;
+        # `frac_executed` is the tensor-pipe utilisation.
         ops = 2 * (5 if ALPHABET == "nucleotide" else 23) * L  # one-hot symbols x positions
         achieved = pairs_per_launch * ops / secs / 1e12
         executed = pairs_per_launch * 2 * mma_k / secs / 1e12
@@ -333,8 +334,10 @@ def main():
     if rank == 0:
         peaks, peaks_kind = load_peaks()
         st = searcher.last_stats
+        # contraction depth per window of the operands the scan really used (union rows: K / 2 per window)
+        mma_k = ctx.last_mma_k or searcher.db.mma_k
         roof = roofline(st["kernel_used"], a.queries * a.db_per_gpu, scan_ms / a.steps, peaks, peaks_kind, clocks, int8_peak,
-                        searcher.db.mma_k)
+                        mma_k)
         out = {
             "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,

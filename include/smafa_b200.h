@@ -234,6 +234,9 @@ int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, const uint3
 /* Contraction depth K (int8 elements per window) of the tcgen05 operands of this db, 0 if the db is
  * not eligible for the MMA kernel: executed int8 ops per comparison = 2 * K. */
 uint32_t smafa_db_mma_k(const smafa_db *db);
+/* The same figure for the operands the LAST tcgen05 scan of this context actually used (union-row operands hold two
+ * windows per row: K / 2 per window); 0 before the first such scan. */
+uint32_t smafa_ctx_last_mma_k(const smafa_ctx *ctx);
 
 #ifdef __cplusplus
 }

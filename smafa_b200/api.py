@@ -97,6 +97,8 @@ def load_library():
     l.smafa_db_file_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
     l.smafa_debug_mma_dump.argtypes = [vp, vp, vp, u64, u32, vp]
     l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
+    l.smafa_ctx_last_mma_k.argtypes = [vp]
+    l.smafa_ctx_last_mma_k.restype = u32
     l.smafa_debug_mma_rate.argtypes = [vp, C.c_int, u32, C.POINTER(C.c_double)]
     l.smafa_debug_sparse_decode.argtypes = [vp, vp, vp, u32, C.c_int, vp]
     l.smafa_db_mma_k.restype = u32
@@ -244,6 +246,11 @@ class Context:
             _raise(rc, self._h)
         return t.value
 
+    @property
+    def last_mma_k(self):
+        """int8 contraction depth per window of the last tcgen05 scan (union-row operands: K / 2); 0 before any."""
+        return int(self._l.smafa_ctx_last_mma_k(self._h))
+
     def mma_rate_ns(self, shape, n_steps=40000):
         """ns per k-step and SM for instruction shape 0 (dense N256), 1 (2 x N128), 2 (sparse K64); see smafa_b200.h."""
         t = C.c_double(0)
@@ -311,6 +318,15 @@ class Db:
     @property
     def size(self):
         return self._l.smafa_db_size(self._h)
+
+    def append(self, enc):
+        """Adds windows at the end of the db (smafa_db_append; cluster grows its centroid db this way)."""
+        e = _words(enc)
+        rc = self._l.smafa_db_append(self.ctx.handle, self._h, e.ctypes.data if e.shape[0] else None, e.shape[0])
+        if rc:
+            _raise(rc, self.ctx.handle)
+        if self.host_words is not None:
+            self.host_words = np.concatenate([self.host_words, e])
 
     @property
     def mma_k(self):

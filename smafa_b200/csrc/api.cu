@@ -102,6 +102,10 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   if (const char *e = getenv("SMAFA_NO_GUESS")) ctx->disable_guess = e[0] == '1';
   if (const char *e = getenv("SMAFA_FORCE_GUESS")) ctx->force_guess = atoi(e);
   if (const char *e = getenv("SMAFA_MMA_NSYM")) ctx->mma_nsym = (e[0] >= '2' && e[0] <= '5') ? (uint32_t)(e[0] - '0') : 3;
+  // union rows are on unless an ablation pins the operand encoding (SMAFA_MMA_NSYM) or asks for single rows
+  ctx->mma_union = SMAFA_MMA_UNION_DEFAULT;
+  if (getenv("SMAFA_MMA_NSYM") != nullptr) ctx->mma_union = 1;
+  if (const char *e = getenv("SMAFA_MMA_UNION")) ctx->mma_union = e[0] == '2' ? 2u : 1u;
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -953,3 +957,5 @@ extern "C" int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, 
   CU(cudaSetDevice(ctx->device));
   return sparse_decode_probe(ctx, a_comp, meta, n_steps, meta_path, out);
 }
+
+extern "C" uint32_t smafa_ctx_last_mma_k(const smafa_ctx *ctx) { return ctx ? ctx->last_mma_k : 0; }

@@ -163,9 +163,17 @@ __device__ __forceinline__ AndTree and_tree32(const uint32_t (&v)[32]) {
 //          half 0 drain while the MMAs of half 1 run, and an accumulator half is refilled as soon as ITS four warps
 //          have read it (four half-buffers in flight instead of two whole ones).  Same tensor cycles per tile
 //          (128*N/256 per instruction), finer hand-over.
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS, bool SPLIT_N>
+// UPR (windows per db operand row) = 2: "union rows".  Row r of the db operand is the OR of the one-hot images of
+//          windows 2r and 2r+1, so D counts the positions where the query base equals EITHER window's base -- an upper
+//          bound of both match counts.  One accumulator then filters two comparisons: half the tensor work and half
+//          the accumulators to drain per comparison.  A survivor row sends both of its windows to the exact re-check.
+//          Between unrelated windows a position passes the union test with probability 7/16 instead of 1/4, so the
+//          filter stays selective only while need = L - bound is large: mma_scan uses these operands when
+//          need >= 3L/4 and the +-1 feature operands otherwise.  One-hot operands only (NSYM = 4).
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS, bool SPLIT_N, int UPR>
 __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
+  static_assert(UPR == 1 || (UPR == 2 && NSYM == 4), "union rows need one-hot operands");
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
   constexpr uint32_t PB = KB / NSYM;         // positions per symbol / feature block
   constexpr uint32_t BIAS_K = NSYM == (int)MMA_ENC_AA ? MMA_ENC_AA * MMA_AA_POS : PB - 1;  // one-hot: symbol A, position PB-1
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         }
       }
       __syncwarp();
-      const uint32_t n = __popc(m0) + __popc(m1);
+      const uint32_t n = (__popc(m0) + __popc(m1)) * UPR;  // ring entries: one per (query, window)
       uint32_t incl, total;
       if ((hitmask & (hitmask - 1)) == 0) {  // one lane holds all the survivors (the common case): no scan
         total = __shfl_sync(0xffffffffu, n, __ffs(hitmask) - 1);
@@ -415,8 +423,11 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         // a flood (bound admits > 1/4 of the chunk): verify straight from the masks, warp-wide per bit
 #pragma unroll 1
         for (int i = 0; i < 32; ++i) {
-          mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row, lane);
-          if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row, lane);
+#pragma unroll
+          for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
+            mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
+            if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
+          }
         }
       } else {
         if (tail + total - head_seen > (uint32_t)MMA_LIST_CAP) {  // ring full: wait for the verifier warp
@@ -431,13 +442,17 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         while (m0) {
           const int i = __ffs(m0) - 1;
           m0 &= m0 - 1;
-          my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row);
+#pragma unroll
+          for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+            my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
         }
         if constexpr (PACK16) {
           while (m1) {
             const int i = __ffs(m1) - 1;
             m1 &= m1 - 1;
-            my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row);
+#pragma unroll
+            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
           }
         }
         tail += total;
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         const uint32_t unit = SPLIT_N ? 2 * buf + part : buf;  // the barrier pair this warp hands over on
         mbar_wait(TFULL(unit), use & 1);
         tc_fence_after();
-        const uint32_t row = t * MMA_M + quarter * 32 + lane;
+        const uint32_t row = t * MMA_M + quarter * 32 + lane;  // db operand row = windows [row * UPR, row * UPR + UPR)
         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * MMA_N + part * COLS_PER_WARP;
         auto load = [&](uint32_t c, uint32_t (&v)[32]) {
           if constexpr (PACK16) tc_ld32_pack16(taddr + c * 64, v);
@@ -597,7 +612,8 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
 // their per-query constant in meta[].
 __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
                                     uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query,
-                                    int need0, int alphabet, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
+                                    int need0, int alphabet, int16_t *__restrict__ meta, uint8_t *__restrict__ out,
+                                    uint32_t upr) {
   const bool aa_exact = enc == MMA_ENC_AA;
   const uint32_t chunks = KB / 16, PB = aa_exact ? MMA_AA_POS : KB / enc, gap = PB - L;
   // thread -> (row, k-chunk): eight consecutive threads take the eight rows of one core-matrix column, whose 16-byte
@@ -606,8 +622,11 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
   const uint32_t t = (uint32_t)(idx % (8 * chunks));
   const uint32_t row = row_begin + (uint32_t)(idx / (8 * chunks)) * 8 + (t & 7), c = t >> 3;
   if (row >= row_end) return;
-  const bool valid = row < n_valid, had = enc <= 3;
-  const uint64_t *w = ref + (size_t)row * W;
+  // upr = 2 (db side of the one-hot encodings only): the row is the union of windows 2*row and 2*row + 1; n_valid
+  // counts windows
+  const bool valid = (uint64_t)row * upr < n_valid, had = enc <= 3;
+  const uint64_t *w = ref + (size_t)row * upr * W;
+  const uint64_t *w2 = (upr == 2 && (uint64_t)row * 2 + 1 < n_valid) ? w + W : nullptr;
   int nN = 0;  // N/gap positions: code 1 = bit 0 of a 5-bit group (protein: symbols of the N-like filter class)
   if (valid) {
     if (alphabet == ALPHA_NUC)
@@ -651,6 +670,7 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
         const uint32_t code = filter_code((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u, alphabet);
         if (!had) {
           v = code == (16u >> f);  // A C G T N
+          if (w2 != nullptr) v |= filter_code((uint32_t)(w2[p / 12] >> (5 * (p % 12))) & 31u, alphabet) == (16u >> f);
         } else if (code >= 2 && (code & (code - 1)) == 0) {
           // A=16 (+,+,+)  C=8 (+,-,-)  G=4 (-,+,-)  T=2 (-,-,+): h, l, h*l
           const uint32_t plus = f == 0 ? (16u | 8u) : (f == 1 ? (16u | 4u) : (16u | 2u));
@@ -683,11 +703,11 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
 
 static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
                                 uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query, int need0,
-                                int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s) {
+                                int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s, uint32_t upr = 1) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)((row_end - row_begin + 7) / 8) * 8 * (KB / 16);
   pack_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
-                                                                enc, is_query, need0, alphabet, meta, out);
+                                                                enc, is_query, need0, alphabet, meta, out, upr);
 }
 
 // Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten
@@ -771,8 +791,34 @@ static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
   return code;
 }
 
+// Union-row operand image (kernel template parameter UPR = 2): 4-symbol one-hot, two windows per row.
+static uint32_t union_kb(const smafa_db *db) { return 4 * mma_pb(4, db->L); }
+static bool union_eligible(const smafa_ctx *ctx, const smafa_db *db) {
+  return ctx->mma_union == 2 && db->alphabet == ALPHA_NUC && mma_enc_ok(4, db->L);
+}
+
+static int union_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
+  const uint64_t tiles = (rows + 2 * MMA_M - 1) / (2 * MMA_M);
+  if (tiles <= db->union_cap) return SMAFA_OK;
+  const size_t tile_bytes = (size_t)MMA_M * union_kb(db);
+  uint8_t *n = nullptr;
+  cudaError_t e = cudaMalloc((void **)&n, tiles * tile_bytes);
+  if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(union-row db operand)", e);
+  if (db->union_img && db->D)
+    cudaMemcpyAsync(n, db->union_img, ((db->D + 2 * MMA_M - 1) / (2 * MMA_M)) * tile_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(db->union_img);
+  db->union_img = n;
+  db->union_cap = tiles;
+  return SMAFA_OK;
+}
+
 int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
   if (db->L == 0 || db->L > 63) return SMAFA_OK;
+  if (union_eligible(ctx, db)) {
+    int rc = union_reserve(ctx, db, rows);
+    if (rc) return rc;
+  }
   const uint64_t tiles = (rows + MMA_M - 1) / MMA_M;
   if (tiles <= db->onehot_cap) return SMAFA_OK;
   const size_t tile_bytes = (size_t)MMA_M * mma_kb(db);
@@ -795,21 +841,27 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
   launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0,
                       db->alphabet, nullptr, db->onehot, ctx->stream);
+  if (db->union_img != nullptr) {  // rows that hold a window of [first, end), then the padding of the last tile
+    const uint32_t r_begin = (uint32_t)(first / 2), r_end = (end + 1) / 2;
+    launch_pack_operand(db->ref, end, r_begin, (r_end + MMA_M - 1) / MMA_M * MMA_M, db->W, db->L, MMA_M, union_kb(db), 4, 0, 0,
+                        db->alphabet, nullptr, db->union_img, ctx->stream, 2);
+  }
   return SMAFA_OK;
 }
 
 void mma_db_free(smafa_db *db) {
   cudaFree(db->onehot);
-  db->onehot = nullptr;
-  db->onehot_cap = 0;
+  cudaFree(db->union_img);
+  db->onehot = db->union_img = nullptr;
+  db->onehot_cap = db->union_cap = 0;
 }
 
-template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2, bool SPLIT_N = false>
+template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2, bool SPLIT_N = false, int UPR = 1>
 static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s) {
   constexpr size_t smem = (size_t)B_BUFS * MMA_N * KSTEPS * 32 + (size_t)STAGES * MMA_M * KSTEPS * 32 + 512 +
                           (size_t)EPI_WARPS * MMA_LIST_CAP * sizeof(uint2);
   static_assert(smem <= 232448, "more than 227 KB of shared memory");
-  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS, SPLIT_N>;
+  auto kern = scan_mma_kernel<KSTEPS, NSYM, STAGES, EPI_WARPS, PACK16, B_BUFS, SPLIT_N, UPR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, mma_threads(EPI_WARPS), smem, s>>>(P);
@@ -817,7 +869,15 @@ static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s)
 }
 
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, int32_t *dump) {
-  const uint32_t KB = mma_kb(db);
+  // Operand choice for this batch: union rows (two windows per accumulator) while the filter stays selective -- the
+  // batch starts at need = L - bound >= 3L/4 (between unrelated windows the union test passes a position with
+  // probability 7/16: at need = 3L/4 of L = 60 that is a 4.9 sigma event, at need = 2L/3 already one row in 6000) --
+  // the +-1 feature operands otherwise.  Bounds only tighten during a scan.
+  const int need_first = std::max(0, (int)p.L - ctx->mma_bound0);
+  const bool use_union = db->union_img != nullptr && 4 * need_first >= 3 * (int)p.L;
+  const uint32_t enc = use_union ? 4u : db->mma_nsym, upr = use_union ? 2u : 1u;
+  const uint32_t KB = use_union ? union_kb(db) : mma_kb(db);
+  ctx->last_mma_k = KB / upr;
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
   const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N * sizeof(int16_t);  // operand tiles + q_meta
   if (ctx->q_onehot_cap < b_bytes) {
@@ -834,14 +894,14 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   MmaParams P{};
   P.sp = p;
   P.need0 = std::max(0, (int)p.L - ctx->mma_bound0);  // the initial bound is uniform over the batch
-  launch_pack_operand(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, db->mma_nsym, 1, P.need0, db->alphabet, meta,
+  launch_pack_operand(p.q_ref, p.Q, 0, n_qtiles * MMA_N, p.W, p.L, MMA_N, KB, enc, 1, P.need0, db->alphabet, meta,
                       ctx->q_onehot, s);
   P.dump = dump;
   P.q_meta = meta;
-  P.a_tiles = db->onehot;
+  P.a_tiles = use_union ? db->union_img : db->onehot;
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
-  P.n_db_tiles = (uint32_t)((db->D + MMA_M - 1) / MMA_M);
+  P.n_db_tiles = (uint32_t)((db->D + MMA_M * upr - 1) / (MMA_M * upr));
   // work items = query tiles x db chunks; aim at a few hundred items per SM-resident CTA for balance
   uint32_t tiles_per_chunk = 128;
   const uint64_t want_items = (uint64_t)ctx->num_sms * 16;
@@ -859,7 +919,12 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint32_t n_items = P.n_qtiles * P.n_chunks;
   const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, n_items);
   cudaError_t e;
-  const bool wide = mma_pb(db->mma_nsym, db->L) == 64;
+  const bool wide = mma_pb(enc, db->L) == 64;
+  if (use_union) {
+    e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s);
+    if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
+    return 2;
+  }
   // Epilogue shape: 8 warps + .pack::16b TMEM loads measured best (profiles/r01_epilogue_variants.txt; the 16-warp
   // shape measured there is gone since the verifier warps took its register budget); SMAFA_MMA_PACK16=0 keeps the
   // unpacked loads of the default encoding reachable.

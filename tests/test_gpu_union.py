@@ -1,0 +1,166 @@
+"""GPU parity of the union-row operands of the tcgen05 scan (scan_mma.cu, UPR = 2): two db windows share one
+accumulator, a surviving row sends both windows to the exact re-check.  Everything is compared with the CPU oracle;
+`ctx.last_mma_k` tells which operands the last scan used (union rows: 2 * positions-per-block per window)."""
+import os
+
+import numpy as np
+import pytest
+
+import smafa_b200
+from oracle import c_oracle
+from smafa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _context(union):
+    old = os.environ.get("SMAFA_MMA_UNION")
+    os.environ["SMAFA_MMA_UNION"] = str(union)
+    try:
+        return smafa_b200.Context(0, "mma")
+    finally:
+        if old is None:
+            os.environ.pop("SMAFA_MMA_UNION", None)
+        else:
+            os.environ["SMAFA_MMA_UNION"] = old
+
+
+@pytest.fixture(scope="module")
+def uctx():
+    from smafa_b200 import build
+    build.build()
+    c_oracle.build()
+    c = _context(2)
+    yield c
+    c.close()
+
+
+def union_k(L):
+    return 2 * (32 if L <= 31 else 64)
+
+
+def check(c, db, q, L, m, k, r=None):
+    d = c.upload(db, L)
+    try:
+        got, st = c.query(d, q, L, max_divergence=m, max_num_hits=k, limit_per_sequence=r, return_stats=True)
+    finally:
+        d.close()
+    want = c_oracle.query(db, L, q, L, m, k, r)
+    assert got.shape == want.shape, (L, m, k, r, got.shape, want.shape)
+    assert (got == want).all(), (L, m, k, r)
+    return st
+
+
+@pytest.mark.parametrize("L,noise", [(20, 0.05), (31, 0.1), (60, 0.05), (63, 0.3)])
+def test_union_accumulators_exact(uctx, L, noise):
+    """Raw accumulators of the first tile: row r = windows 2r, 2r+1; D = #positions where the query base equals either
+    window's base, minus max(0, need - nN_q).  999 windows: the last row of the db holds a single window."""
+    db_sym = synth.make_db(999, L=L, seed=11, noise=noise)
+    q_sym = synth.make_queries(db_sym, 256, seed=12, noise=noise)
+    d = uctx.upload(synth.pack_symbols(db_sym), L)
+    bound = L // 5                                   # need = L - bound >= 3L/4: the union operands are selected
+    acc = uctx.debug_mma_dump(d, synth.pack_symbols(q_sym), bound)
+    assert uctx.last_mma_k == union_k(L)
+    w1, w2 = db_sym[0:256:2], db_sym[1:256:2]
+    qb = q_sym[None, :, :]
+    hit = ((qb == w1[:, None, :]) | (qb == w2[:, None, :])) & (qb < 4)
+    nq = (q_sym == 4).sum(axis=1)
+    want = hit.sum(axis=2).astype(np.int32) - np.maximum(0, np.minimum((L - bound) - nq, 127))[None, :].astype(np.int32)
+    assert (acc == want).all()
+    # conservative for both windows of a row
+    for w in (w1, w2):
+        dist = (w[:, None, :] != q_sym[None, :, :]).sum(axis=2)
+        assert (acc[dist <= bound] >= 0).all()
+    d.close()
+
+
+MODES = [(3, None, None), (0, None, None), (5, 10, None), (2, 50, None), (None, None, None), (None, 10, None),
+         (8, 25, 2), (99, 99, None)]
+
+
+@pytest.mark.parametrize("L", [9, 20, 31, 32, 33, 60, 63])
+def test_union_query_matches_oracle(uctx, L):
+    db_sym = synth.make_db(3001, L=L, seed=300 + L, family=8, max_subs=min(4, L), noise=0.03)   # odd: a half-filled row
+    q_sym = synth.make_queries(db_sym, 300, seed=400 + L, max_subs=min(6, L), noise=0.03)
+    db, q = synth.pack_symbols(db_sym), synth.pack_symbols(q_sym)
+    used = set()
+    for m, k, r in MODES + [(L // 4, 5000, None)]:
+        st = check(uctx, db, q, L, m, k, r)
+        assert st["kernel_used"] == 2
+        used.add(uctx.last_mma_k)
+    assert union_k(L) in used                        # the tight modes ran on the union rows
+    assert len(used) == 2                            # and the loose ones on the single-window operands
+
+
+def test_union_ties_floods_and_tiny_shapes(uctx):
+    L = 60
+    one = synth.random_symbols(1, L, seed=1)
+    same = synth.pack_symbols(np.repeat(one, 701, axis=0))   # every pair survives: flood path, both windows of every row
+    q_sym = np.repeat(one, 320, axis=0)
+    q_sym[::4] = synth.random_symbols(len(q_sym[::4]), L, seed=22)
+    q = synth.pack_symbols(q_sym)
+    for m, k, r in [(0, None, None), (4, 2000, None), (3, 3, 2), (5, 700, None)]:
+        check(uctx, same, q, L, m, k, r)
+        assert uctx.last_mma_k == 128
+    check(uctx, synth.pack_symbols(one), q, L, 2, None)        # D = 1: one row, one window
+    check(uctx, same[:2], q, L, 2, 5)                          # D = 2: one full row
+
+
+def test_union_survivor_rings_under_pressure(uctx):
+    L = 60
+    fam = synth.make_db(40_001, L=L, seed=23, family=400, max_subs=6, noise=0.0)
+    qf = synth.make_queries(fam, 512, seed=24, max_subs=4, noise=0.0)
+    dbw, qw = synth.pack_symbols(fam), synth.pack_symbols(qf)
+    for m, k in [(12, 40_000), (14, None), (15, 300)]:
+        st = check(uctx, dbw, qw, L, m, k)
+        assert uctx.last_mma_k == 128
+    assert st["candidates"] >= 300 * 512
+    uctx.set_candidate_capacity(4096)
+    try:
+        st = check(uctx, dbw, qw, L, 10, 6000)                 # overflow -> the batch is split and scanned again
+        assert st["retries"] > 0
+    finally:
+        uctx.set_candidate_capacity(0)
+
+
+@pytest.mark.parametrize("L,t,n", [(60, 3, 20000), (20, 1, 5000), (33, 6, 4000)])
+def test_union_cluster_matches_oracle(uctx, L, t, n):
+    """The centroid db grows by appends of any parity: a union row is re-packed when its second window arrives."""
+    sym = synth.make_cluster_input(n, L=L, seed=700 + L, family=10, max_subs=min(3, L))
+    enc_all = synth.pack_symbols(sym)
+    want_cof, want_nc, want_cmp = c_oracle.cluster(enc_all, L, t)
+    keep = want_cof >= 0
+    enc = enc_all[keep]
+    remap = np.cumsum(keep) - 1
+    cof, nc, ncmp = uctx.cluster(enc, L, t)
+    assert nc == want_nc and ncmp == want_cmp
+    assert (cof.astype(np.int64) == remap[want_cof[keep]]).all()
+
+
+def test_union_append_parity(uctx):
+    """smafa_db_append with odd and even starting sizes equals one upload of the whole db."""
+    L = 60
+    db_sym = synth.make_db(1500, L=L, seed=41)
+    q = synth.pack_symbols(synth.make_queries(db_sym, 128, seed=42))
+    db = synth.pack_symbols(db_sym)
+    d = uctx.upload(db[:301], L)
+    for a, b in [(301, 302), (302, 555), (555, 1000), (1000, 1500)]:
+        d.append(db[a:b])
+    got = uctx.query(d, q, L, max_divergence=6, max_num_hits=7)
+    assert uctx.last_mma_k == 128
+    d.close()
+    want = c_oracle.query(db, L, q, L, 6, 7, None)
+    assert got.shape == want.shape and (got == want).all()
+
+
+def test_single_rows_still_selectable():
+    """SMAFA_MMA_UNION=1 keeps the +-1 feature operands for every bound."""
+    L = 60
+    c = _context(1)
+    try:
+        db_sym = synth.make_db(2000, L=L, seed=51)
+        q = synth.pack_symbols(synth.make_queries(db_sym, 200, seed=52))
+        check(c, synth.pack_symbols(db_sym), q, L, 5, 10)
+        assert c.last_mma_k == 192
+    finally:
+        c.close()
