@@ -1,4 +1,4 @@
-# One GPU call: parity of the union-row operands (tests/test_gpu_union.py), then benches next to the default kernel.
+# One GPU call: parity of the union-row operands (tests/test_gpu_union.py), then benches with the degree picked per scan.
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
 nvidia-smi -L
@@ -14,12 +14,11 @@ except Exception as e:
     print("  $name unreadable:", e)
 PY
 }
-run m5_besthit_single      SMAFA_MMA_UNION=1 $B
-run m5_besthit_union       SMAFA_MMA_UNION=2 $B
-run m5_top10_union         SMAFA_MMA_UNION=2 $B --mode b
-run unbounded_top10_union  SMAFA_MMA_UNION=2 $B --mode b --max-divergence none
-run unbounded_besthit_union SMAFA_MMA_UNION=2 $B --max-divergence none
-run m10_top10_union        SMAFA_MMA_UNION=2 $B --mode b --max-divergence 10
-run m15_top10_union        SMAFA_MMA_UNION=2 $B --mode b --max-divergence 15
-run m15_top10_single       SMAFA_MMA_UNION=1 $B --mode b --max-divergence 15
-run l30_m5_union           SMAFA_MMA_UNION=2 $B --window-length 30
+run m5_besthit_auto        SMAFA_MMA_UNION=3 $B
+run m5_besthit_force2      SMAFA_MMA_UNION_FORCE=2 $B
+run m5_top10_auto          SMAFA_MMA_UNION=3 $B --mode b
+run m10_top10_auto         SMAFA_MMA_UNION=3 $B --mode b --max-divergence 10
+run m15_top10_auto         SMAFA_MMA_UNION=3 $B --mode b --max-divergence 15
+run unbounded_besthit_auto SMAFA_MMA_UNION=3 $B --max-divergence none
+run unbounded_top10_auto   SMAFA_MMA_UNION=3 $B --mode b --max-divergence none
+run l30_m5_auto            SMAFA_MMA_UNION=3 $B --window-length 30

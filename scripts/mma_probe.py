@@ -5,6 +5,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("SMAFA_MMA_UNION", "1")  # this probe models the single-window operands
 import smafa_b200
 from smafa_b200 import synth
 

@@ -105,7 +105,8 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   // union rows are on unless an ablation pins the operand encoding (SMAFA_MMA_NSYM) or asks for single rows
   ctx->mma_union = SMAFA_MMA_UNION_DEFAULT;
   if (getenv("SMAFA_MMA_NSYM") != nullptr) ctx->mma_union = 1;
-  if (const char *e = getenv("SMAFA_MMA_UNION")) ctx->mma_union = e[0] == '2' ? 2u : 1u;
+  if (const char *e = getenv("SMAFA_MMA_UNION")) ctx->mma_union = (e[0] >= '1' && e[0] <= '3') ? (uint32_t)(e[0] - '0') : 1u;
+  if (const char *e = getenv("SMAFA_MMA_UNION_FORCE")) ctx->mma_union_force = atoi(e);
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -412,6 +413,47 @@ static int guess_bound(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref
   return g;
 }
 
+// How many db windows share one accumulator in the next tcgen05 scan (scan_mma.cu, UPR).  A union row of u windows
+// costs 1/u of the tensor work and of the accumulator drain per comparison, but every row that passes its (looser)
+// filter sends u windows to the exact re-check.  Per comparison:  cost(u) = t_u + c_v * f_u,  t_u = scan time per
+// comparison measured on B200 at L = 60 (100 k x 1 M: 9.6 ms, 6.4 ms, ~4.3 ms per 1e11), c_v = 1.5 ns per verified
+// window, f_u = fraction of the rows of degree u that pass at need = L - b0 -- measured on a
+// strided sample of this batch against this db, so related windows, skewed base composition or a loose bound
+// simply show up as a larger f_u and a smaller degree.  Small batches use the thresholds the model gives for
+// unrelated uniform windows (pass probability 7/16 or 37/64 per position: need >= 3L/4, 7L/8).
+static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint32_t nq, int b0, cudaStream_t s,
+                                  int *launches, int *rc_out) {
+  *rc_out = SMAFA_OK;
+  uint32_t max_u = 1;
+  for (uint32_t u = 2; u <= 3; ++u)
+    if (db->union_img[u - 2] != nullptr) max_u = u;
+  const int need = (int)db->L - b0;
+  if (max_u == 1 || need <= 0) return 1;
+  if (ctx->mma_union_force >= 1) return std::min<uint32_t>((uint32_t)ctx->mma_union_force, max_u);
+  const double pairs = (double)nq * (double)db->D;
+  if (pairs < 2e9 || db->D < 65536 || nq < 1024) {
+    if (max_u >= 3 && 8 * need >= 7 * (int)db->L) return 3;
+    return 4 * need >= 3 * (int)db->L ? 2 : 1;
+  }
+  const uint32_t q_stride = (nq + 8191) / 8192;
+  const uint32_t n_d = (uint32_t)std::min<uint64_t>(2048, db->D);
+  const uint32_t d_stride = (uint32_t)(db->D / n_d);
+  unsigned long long *counts = ctx->d_scalars + 8;  // shared with the guess histogram: both are read back before reuse
+  *launches += launch_union_sample(q_dev, nq, q_stride, db->ref, (uint32_t)db->D, d_stride, n_d, db->W, need, counts, s);
+  cudaError_t e = cudaMemcpyAsync(ctx->h_scalars + 8, counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { *rc_out = fail(ctx, SMAFA_E_CUDA, "union sample: %s", cudaGetErrorString(e)); return 1; }
+  const double n_s = std::max<double>(1.0, (double)ctx->h_scalars[11]);
+  static const double t_u[3] = {9.6e-5, 6.4e-5, 4.3e-5};  // ns per comparison
+  uint32_t best = 1;
+  double best_cost = 0;
+  for (uint32_t u = 1; u <= max_u; ++u) {
+    const double cost = t_u[u - 1] + 1.5 * (double)ctx->h_scalars[8 + u - 1] / n_s;
+    if (u == 1 || cost < best_cost) { best = u; best_cost = cost; }
+  }
+  return best;
+}
+
 // One batch (<= 2^20 queries, words already on the device).  Leaves *n_rows rows in ctx->hits.
 static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
                      const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st) {
@@ -485,6 +527,8 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
     }
     if (kern == SMAFA_KERNEL_MMA) {
       ctx->mma_bound0 = b0;
+      ctx->mma_union_pick = pick_union_degree(ctx, db, q_dev, nq, b0, s, &launches, &r);
+      if (r) return r;
       int l = mma_scan(ctx, db, p, s, ctx->mma_dump);
       if (l < 0) return l;
       launches += l;

@@ -78,6 +78,82 @@ int launch_sample_hist(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, con
 }
 int guess_bins() { return GUESS_BINS; }
 
+// ---- selectivity of the union-row filter (scan_mma.cu, UPR) on this batch -------------------------------------------
+// counts[u-1] += number of sampled (query, db operand row of u windows) pairs that pass the filter at need = L - bound,
+// u = 1, 2, 3: base matches with ANY window of the row >= need - nN_q (nN_q = the query's N/gap positions), which is
+// exactly the sign test of the one-hot tcgen05 operands (the +-1 feature operands of u = 1 are at least as tight).
+// On the reference's 5-bit one-hot codes (src/lib.rs:167-184) the base matches of q and w are popcount(q & w) over
+// the four base bits of every group, and a union row is the OR of its windows.  The sampled row of degree u is the one
+// that holds window j (every d_stride-th window), so the sample sees the db's real neighbour structure.
+// counts[3] += samples.  Thread = sampled query; blockIdx.y = slice of the sampled windows (uniform loads).
+template <int W>
+__global__ void __launch_bounds__(GUESS_THREADS) union_sample_kernel(const uint64_t *__restrict__ q_ref, uint32_t Q, uint32_t q_stride,
+                                                                     const uint64_t *__restrict__ d_ref, uint32_t D,
+                                                                     uint32_t d_stride, uint32_t n_d, uint32_t per_block, int need,
+                                                                     unsigned long long *__restrict__ counts) {
+  constexpr uint64_t NBITS = 0x0084210842108421ull;  // bit 0 of every 5-bit group: code 1 = N / gap / IUPAC
+  const uint64_t q = (uint64_t)(blockIdx.x * GUESS_THREADS + threadIdx.x) * q_stride;
+  uint64_t qw[W];
+  int nN = 0;
+#pragma unroll
+  for (int x = 0; x < W; ++x) {
+    const uint64_t v = q < Q ? q_ref[q * W + x] : 0;
+    nN += __popcll(v & NBITS);
+    qw[x] = v & ~NBITS;
+  }
+  const int thr = q < Q ? need - nN : 1 << 20;
+  uint32_t n1 = 0, n2 = 0, n3 = 0, ns = 0;
+  const uint32_t i_end = min(n_d, (blockIdx.y + 1) * per_block);
+  for (uint32_t i = blockIdx.y * per_block; i < i_end; ++i) {
+    const uint32_t j = i * d_stride, p0 = j & ~1u, t0 = j / 3 * 3;
+    int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int x = 0; x < W; ++x) {
+      const uint64_t a = d_ref[(uint64_t)p0 * W + x], b = p0 + 1 < D ? d_ref[(uint64_t)(p0 + 1) * W + x] : 0;
+      uint64_t t = d_ref[(uint64_t)t0 * W + x];
+      if (t0 + 1 < D) t |= d_ref[(uint64_t)(t0 + 1) * W + x];
+      if (t0 + 2 < D) t |= d_ref[(uint64_t)(t0 + 2) * W + x];
+      c1 += __popcll(qw[x] & ((j & 1u) ? b : a));
+      c2 += __popcll(qw[x] & (a | b));
+      c3 += __popcll(qw[x] & t);
+    }
+    n1 += c1 >= thr;
+    n2 += c2 >= thr;
+    n3 += c3 >= thr;
+    ns += q < Q;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, d);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, d);
+    n3 += __shfl_xor_sync(0xffffffffu, n3, d);
+    ns += __shfl_xor_sync(0xffffffffu, ns, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n1) atomicAdd(counts + 0, (unsigned long long)n1);
+    if (n2) atomicAdd(counts + 1, (unsigned long long)n2);
+    if (n3) atomicAdd(counts + 2, (unsigned long long)n3);
+    if (ns) atomicAdd(counts + 3, (unsigned long long)ns);
+  }
+}
+
+int launch_union_sample(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D, uint32_t d_stride,
+                        uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s) {
+  const uint32_t n_q = (Q + q_stride - 1) / q_stride;
+  const uint32_t per_block = 64;
+  const dim3 grid((n_q + GUESS_THREADS - 1) / GUESS_THREADS, (n_d + per_block - 1) / per_block);
+  cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s);
+  switch (W) {
+    case 1: union_sample_kernel<1><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 2: union_sample_kernel<2><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 3: union_sample_kernel<3><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 4: union_sample_kernel<4><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 5: union_sample_kernel<5><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    default: union_sample_kernel<6><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+  }
+  return 1;
+}
+
 // per_query[q] = number of candidates of query q
 __global__ void count_per_query_kernel(const uint64_t *__restrict__ cand, uint64_t n, uint32_t *__restrict__ per_query) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)

@@ -7,8 +7,8 @@
 #include "kernels.h"
 
 constexpr uint64_t DEFAULT_CAND_CAP = 32ull << 20;     // largest candidate workspace allocated up front (rows, 8 B keys)
-// Default of smafa_ctx::mma_union (1 = single rows).  Union rows are opt-in (SMAFA_MMA_UNION=2) until measured on B200.
-constexpr uint32_t SMAFA_MMA_UNION_DEFAULT = 1;
+// Default of smafa_ctx::mma_union: the largest union degree (windows per accumulator) dbs are packed for.
+constexpr uint32_t SMAFA_MMA_UNION_DEFAULT = 3;
 constexpr uint64_t MAX_AUTO_CAND_CAP = 256ull << 20;  // largest the workspace grows to on its own before a batch is split
 
 struct smafa_ctx {
@@ -20,7 +20,9 @@ struct smafa_ctx {
   // rate does not depend on how tight the bound is.  Tiny query batches stay on the POPC kernel.
   bool auto_prefers_mma = true;
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
-  uint32_t mma_union = 1;         // 2: dbs also get the union-row operand image (two windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
+  uint32_t mma_union = 1;         // largest union degree dbs get operand images for (1..3 windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
+  int mma_union_force = 0;        // SMAFA_MMA_UNION_FORCE=u: every tcgen05 scan uses degree u whatever the sample says (tests)
+  uint32_t mma_union_pick = 1;    // degree of the next mma_scan (set per scan by run_batch)
   uint32_t last_mma_k = 0;        // int8 contraction depth per WINDOW of the last tcgen05 scan (K / windows per row)
   int alphabet = 0;               // Alphabet of the dbs uploaded next and of smafa_cluster input (smafa_ctx_set_alphabet)
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
@@ -70,8 +72,8 @@ struct smafa_db {
   uint8_t *onehot = nullptr;
   uint32_t mma_nsym = 3;      // encoding of `onehot` (mma_pick_encoding)
   uint64_t onehot_cap = 0;
-  uint8_t *union_img = nullptr;  // union-row image: [tiles of 256 windows][128 rows * 4 PB bytes], or nullptr
-  uint64_t union_cap = 0;        // in tiles
+  uint8_t *union_img[2] = {nullptr, nullptr};  // union-row images of degree 2, 3: [tiles of 128*u windows][128 rows * 4 PB bytes]
+  uint64_t union_cap[2] = {0, 0};              // in tiles
 };
 
 const char *smafa_global_error();

@@ -27,6 +27,10 @@ int popc_tile_rows();
 int launch_sample_hist(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t d_stride,
                        uint32_t n_d, uint32_t W, int alphabet, unsigned long long *ghist, cudaStream_t s);
 int guess_bins();
+// Selectivity of the union-row filter of degree 1..3 at need = L - bound on a strided sample: counts[0..2] = passing
+// (query, row) pairs, counts[3] = samples (guess.cu)
+int launch_union_sample(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D, uint32_t d_stride,
+                        uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s);
 void launch_count_per_query(const uint64_t *cand, uint64_t n, uint32_t Q, uint32_t *per_query, cudaStream_t s);
 void launch_list_unfinished(const uint32_t *per_query, uint32_t Q, uint32_t need, uint32_t *list, uint32_t *n_list, cudaStream_t s);
 void launch_gather_queries(const uint64_t *q_ref, const uint32_t *list, uint32_t n, uint32_t W, uint64_t *out, cudaStream_t s);

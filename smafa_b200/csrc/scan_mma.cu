@@ -163,17 +163,18 @@ __device__ __forceinline__ AndTree and_tree32(const uint32_t (&v)[32]) {
 //          half 0 drain while the MMAs of half 1 run, and an accumulator half is refilled as soon as ITS four warps
 //          have read it (four half-buffers in flight instead of two whole ones).  Same tensor cycles per tile
 //          (128*N/256 per instruction), finer hand-over.
-// UPR (windows per db operand row) = 2: "union rows".  Row r of the db operand is the OR of the one-hot images of
-//          windows 2r and 2r+1, so D counts the positions where the query base equals EITHER window's base -- an upper
-//          bound of both match counts.  One accumulator then filters two comparisons: half the tensor work and half
-//          the accumulators to drain per comparison.  A survivor row sends both of its windows to the exact re-check.
-//          Between unrelated windows a position passes the union test with probability 7/16 instead of 1/4, so the
-//          filter stays selective only while need = L - bound is large: mma_scan uses these operands when
-//          need >= 3L/4 and the +-1 feature operands otherwise.  One-hot operands only (NSYM = 4).
+// UPR (windows per db operand row) = 2 or 3: "union rows".  Row r of the db operand is the OR of the one-hot images
+//          of windows UPR*r .. UPR*r + UPR-1, so D counts the positions where the query base equals ANY of their
+//          bases -- an upper bound of every one of their match counts.  One accumulator then filters UPR comparisons:
+//          1/UPR of the tensor work and of the accumulators to drain per comparison.  A survivor row sends all of its
+//          windows to the exact re-check.  Between unrelated windows a position passes the union test with probability
+//          1 - (3/4)^UPR (7/16, 37/64) instead of 1/4, so the filter is selective only while need = L - bound is
+//          large; the caller picks UPR per scan from a sample of the batch (api.cu pick_union_degree).  One-hot
+//          operands only (NSYM = 4).
 template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS, bool SPLIT_N, int UPR>
 __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
-  static_assert(UPR == 1 || (UPR == 2 && NSYM == 4), "union rows need one-hot operands");
+  static_assert(UPR == 1 || ((UPR == 2 || UPR == 3) && NSYM == 4), "union rows need one-hot operands");
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
   constexpr uint32_t PB = KB / NSYM;         // positions per symbol / feature block
   constexpr uint32_t BIAS_K = NSYM == (int)MMA_ENC_AA ? MMA_ENC_AA * MMA_AA_POS : PB - 1;  // one-hot: symbol A, position PB-1
@@ -622,11 +623,11 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
   const uint32_t t = (uint32_t)(idx % (8 * chunks));
   const uint32_t row = row_begin + (uint32_t)(idx / (8 * chunks)) * 8 + (t & 7), c = t >> 3;
   if (row >= row_end) return;
-  // upr = 2 (db side of the one-hot encodings only): the row is the union of windows 2*row and 2*row + 1; n_valid
-  // counts windows
+  // upr > 1 (db side of the one-hot encodings only): the row is the union of windows upr*row .. upr*row + upr-1;
+  // n_valid counts windows
   const bool valid = (uint64_t)row * upr < n_valid, had = enc <= 3;
   const uint64_t *w = ref + (size_t)row * upr * W;
-  const uint64_t *w2 = (upr == 2 && (uint64_t)row * 2 + 1 < n_valid) ? w + W : nullptr;
+  const uint32_t extra = valid ? (uint32_t)min((uint64_t)upr, (uint64_t)n_valid - (uint64_t)row * upr) - 1 : 0;  // further windows of the row
   int nN = 0;  // N/gap positions: code 1 = bit 0 of a 5-bit group (protein: symbols of the N-like filter class)
   if (valid) {
     if (alphabet == ALPHA_NUC)
@@ -670,7 +671,8 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
         const uint32_t code = filter_code((uint32_t)(w[p / 12] >> (5 * (p % 12))) & 31u, alphabet);
         if (!had) {
           v = code == (16u >> f);  // A C G T N
-          if (w2 != nullptr) v |= filter_code((uint32_t)(w2[p / 12] >> (5 * (p % 12))) & 31u, alphabet) == (16u >> f);
+          for (uint32_t u = 1; u <= extra; ++u)
+            v |= filter_code((uint32_t)(w[u * W + p / 12] >> (5 * (p % 12))) & 31u, alphabet) == (16u >> f);
         } else if (code >= 2 && (code & (code - 1)) == 0) {
           // A=16 (+,+,+)  C=8 (+,-,-)  G=4 (-,+,-)  T=2 (-,-,+): h, l, h*l
           const uint32_t plus = f == 0 ? (16u | 8u) : (f == 1 ? (16u | 4u) : (16u | 2u));
@@ -791,32 +793,33 @@ static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
   return code;
 }
 
-// Union-row operand image (kernel template parameter UPR = 2): 4-symbol one-hot, two windows per row.
+// Union-row operand images (kernel template parameter UPR = 2, 3): 4-symbol one-hot, UPR windows per row.
 static uint32_t union_kb(const smafa_db *db) { return 4 * mma_pb(4, db->L); }
-static bool union_eligible(const smafa_ctx *ctx, const smafa_db *db) {
-  return ctx->mma_union == 2 && db->alphabet == ALPHA_NUC && mma_enc_ok(4, db->L);
+static uint32_t union_max_degree(const smafa_ctx *ctx, const smafa_db *db) {
+  return (db->alphabet == ALPHA_NUC && mma_enc_ok(4, db->L)) ? std::min<uint32_t>(ctx->mma_union, 3) : 1;
 }
 
-static int union_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
-  const uint64_t tiles = (rows + 2 * MMA_M - 1) / (2 * MMA_M);
-  if (tiles <= db->union_cap) return SMAFA_OK;
+static int union_reserve(smafa_ctx *ctx, smafa_db *db, uint32_t upr, uint64_t rows) {
+  const uint64_t per_tile = (uint64_t)upr * MMA_M;
+  const uint64_t tiles = (rows + per_tile - 1) / per_tile;
+  uint8_t *&img = db->union_img[upr - 2];
+  if (tiles <= db->union_cap[upr - 2]) return SMAFA_OK;
   const size_t tile_bytes = (size_t)MMA_M * union_kb(db);
   uint8_t *n = nullptr;
   cudaError_t e = cudaMalloc((void **)&n, tiles * tile_bytes);
   if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_OOM, "cudaMalloc(union-row db operand)", e);
-  if (db->union_img && db->D)
-    cudaMemcpyAsync(n, db->union_img, ((db->D + 2 * MMA_M - 1) / (2 * MMA_M)) * tile_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (img && db->D) cudaMemcpyAsync(n, img, ((db->D + per_tile - 1) / per_tile) * tile_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(db->union_img);
-  db->union_img = n;
-  db->union_cap = tiles;
+  cudaFree(img);
+  img = n;
+  db->union_cap[upr - 2] = tiles;
   return SMAFA_OK;
 }
 
 int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
   if (db->L == 0 || db->L > 63) return SMAFA_OK;
-  if (union_eligible(ctx, db)) {
-    int rc = union_reserve(ctx, db, rows);
+  for (uint32_t upr = 2; upr <= union_max_degree(ctx, db); ++upr) {
+    int rc = union_reserve(ctx, db, upr, rows);
     if (rc) return rc;
   }
   const uint64_t tiles = (rows + MMA_M - 1) / MMA_M;
@@ -841,19 +844,24 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
   launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0,
                       db->alphabet, nullptr, db->onehot, ctx->stream);
-  if (db->union_img != nullptr) {  // rows that hold a window of [first, end), then the padding of the last tile
-    const uint32_t r_begin = (uint32_t)(first / 2), r_end = (end + 1) / 2;
+  for (uint32_t upr = 2; upr <= 3; ++upr) {  // rows that hold a window of [first, end), then the padding of the last tile
+    if (db->union_img[upr - 2] == nullptr) continue;
+    const uint32_t r_begin = (uint32_t)(first / upr), r_end = (end + upr - 1) / upr;
     launch_pack_operand(db->ref, end, r_begin, (r_end + MMA_M - 1) / MMA_M * MMA_M, db->W, db->L, MMA_M, union_kb(db), 4, 0, 0,
-                        db->alphabet, nullptr, db->union_img, ctx->stream, 2);
+                        db->alphabet, nullptr, db->union_img[upr - 2], ctx->stream, upr);
   }
   return SMAFA_OK;
 }
 
 void mma_db_free(smafa_db *db) {
   cudaFree(db->onehot);
-  cudaFree(db->union_img);
-  db->onehot = db->union_img = nullptr;
-  db->onehot_cap = db->union_cap = 0;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(db->union_img[i]);
+    db->union_img[i] = nullptr;
+    db->union_cap[i] = 0;
+  }
+  db->onehot = nullptr;
+  db->onehot_cap = 0;
 }
 
 template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS = 2, bool SPLIT_N = false, int UPR = 1>
@@ -869,13 +877,12 @@ static cudaError_t launch_mma(const MmaParams &P, uint32_t grid, cudaStream_t s)
 }
 
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, int32_t *dump) {
-  // Operand choice for this batch: union rows (two windows per accumulator) while the filter stays selective -- the
-  // batch starts at need = L - bound >= 3L/4 (between unrelated windows the union test passes a position with
-  // probability 7/16: at need = 3L/4 of L = 60 that is a 4.9 sigma event, at need = 2L/3 already one row in 6000) --
-  // the +-1 feature operands otherwise.  Bounds only tighten during a scan.
-  const int need_first = std::max(0, (int)p.L - ctx->mma_bound0);
-  const bool use_union = db->union_img != nullptr && 4 * need_first >= 3 * (int)p.L;
-  const uint32_t enc = use_union ? 4u : db->mma_nsym, upr = use_union ? 2u : 1u;
+  // Operand choice for this scan: ctx->mma_union_pick windows per db operand row (api.cu pick_union_degree), if this
+  // db holds that image; the db's own encoding (+-1 features by default) with one window per row otherwise.
+  uint32_t upr = ctx->mma_union_pick;
+  if (upr < 2 || upr > 3 || db->union_img[upr - 2] == nullptr) upr = 1;
+  const bool use_union = upr > 1;
+  const uint32_t enc = use_union ? 4u : db->mma_nsym;
   const uint32_t KB = use_union ? union_kb(db) : mma_kb(db);
   ctx->last_mma_k = KB / upr;
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
@@ -898,7 +905,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
                       ctx->q_onehot, s);
   P.dump = dump;
   P.q_meta = meta;
-  P.a_tiles = use_union ? db->union_img : db->onehot;
+  P.a_tiles = use_union ? db->union_img[upr - 2] : db->onehot;
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
   P.n_db_tiles = (uint32_t)((db->D + MMA_M * upr - 1) / (MMA_M * upr));
@@ -921,7 +928,8 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   cudaError_t e;
   const bool wide = mma_pb(enc, db->L) == 64;
   if (use_union) {
-    e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s);
+    if (upr == 2) e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s);
+    else e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 3>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 3>(P, grid, s);
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
     return 2;
   }
