@@ -37,10 +37,13 @@ Q_DEFAULT = 100_000
 D_PER_GPU = 1_000_000
 MAX_DIVERGENCE = 5
 ALPHABET = "nucleotide"
-# dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full)
-MMA_TRAFFIC_BYTES = 230.0e6 + 4.9e6
-MMA_TRAFFIC_SOURCE = ("ncu dram__bytes_read+write, profiles/r01_ncu_mma_v8_summary.txt (algorithmic: 192 MB "
-                      "db operand tiles + 19 MB query tiles, read once)")
+# dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full),
+# keyed by the contraction depth per window of the operands that ran (192: +-1 feature operands, one window per row;
+# 85: one-hot union rows, three windows per accumulator).  Other operand choices have no capture: traffic = null.
+MMA_TRAFFIC = {
+    192: (230.0e6 + 4.9e6, "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v8_summary.txt (algorithmic: 192 MB "
+                           "db operand tiles + 19 MB query tiles, read once)"),
+}
 
 
 def parse_args():
@@ -199,12 +202,16 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
         # issue-only tcgen05 kind::i8 probe (smafa_debug_mma_peak) on this GPU, same clocks.
         return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s",
                 "unit_note": "integer path: 1 'FLOP' here = one int8 multiply or add on the tensor pipe (TOP/s)",
-                "frac": achieved / int8_peak, "traffic": MMA_TRAFFIC_BYTES,
+                "frac": achieved / int8_peak, "traffic": MMA_TRAFFIC.get(mma_k, (None, None))[0],
                 "peak_source": "measured in this run: tcgen05.mma kind::i8 M128xN256xK32 issue-only probe "
                                f"on all SMs; for reference 2 x {peaks_kind} bf16_tflops = {2 * peaks['bf16_tflops']:.0f}",
                 "ops_per_comparison": ops, "executed_ops_per_comparison": 2 * mma_k,
                 "achieved_executed": executed, "frac_executed": executed / int8_peak,
-                "traffic_source": MMA_TRAFFIC_SOURCE}
+                "traffic_source": MMA_TRAFFIC.get(mma_k, (None, "no ncu capture for these operands"))[1],
+                "operands": {192: "+-1 character features, one window per accumulator (K = 192)",
+                             128: "one-hot union rows, two windows per accumulator (K = 256 per row)",
+                             85: "one-hot union rows, three windows per accumulator (K = 256 per row)"}.get(
+                                 mma_k, f"K = {mma_k} per window")}
     # POPC formulation: the binding unit is the POPC pipe.  Reference layout = 10 x (XOR32+POPC32)
     # per comparison (5 u64 words, src/lib.rs:85).  The bit-plane packing needs 2 (1 with early exit).
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0

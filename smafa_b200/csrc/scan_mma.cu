@@ -928,6 +928,13 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   cudaError_t e;
   const bool wide = mma_pb(enc, db->L) == 64;
   if (use_union) {
+    // SMAFA_MMA_UNION_STAGES4=1 (ablation): one query operand buffer and four db tile stages instead of two and two
+    static const bool stages4 = getenv("SMAFA_MMA_UNION_STAGES4") ? atoi(getenv("SMAFA_MMA_UNION_STAGES4")) != 0 : false;
+    if (stages4 && wide) {
+      e = upr == 2 ? launch_mma<8, 4, 4, 8, true, 1, false, 2>(P, grid, s) : launch_mma<8, 4, 4, 8, true, 1, false, 3>(P, grid, s);
+      if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
+      return 2;
+    }
     if (upr == 2) e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s);
     else e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 3>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 3>(P, grid, s);
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
