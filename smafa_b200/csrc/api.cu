@@ -428,16 +428,17 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
   for (uint32_t u = 2; u <= 3; ++u)
     if (db->union_img[u - 2] != nullptr) max_u = u;
   const int need = (int)db->L - b0;
-  if (max_u == 1 || need <= 0) return 1;
+  if (max_u == 1 || 2 * need < (int)db->L) return 1;  // a union of two windows differs from a query in < L/2 positions far too often
   if (ctx->mma_union_force >= 1) return std::min<uint32_t>((uint32_t)ctx->mma_union_force, max_u);
   const double pairs = (double)nq * (double)db->D;
   if (pairs < 2e9 || db->D < 65536 || nq < 1024) {
     if (max_u >= 3 && 8 * need >= 7 * (int)db->L) return 3;
     return 4 * need >= 3 * (int)db->L ? 2 : 1;
   }
-  // 4096 x 2048 = 8.4 M sampled pairs: one count is 1.2e-7 of the rows, i.e. 1.8e-7 ns in the cost below
+  // 4096 x 1024 = 4.2 M sampled pairs: one count is 2.4e-7 of the rows, i.e. 3.6e-7 ns in the cost below (the t_u are
+  // 2e-5 apart); ncu: 81 us per launch at 4096 x 2048 (profiles/r01_launches_v9_summary.txt), 1.9 % of a 100 k x 1 M step
   const uint32_t q_stride = (nq + 4095) / 4096;
-  const uint32_t n_d = (uint32_t)std::min<uint64_t>(2048, db->D);
+  const uint32_t n_d = (uint32_t)std::min<uint64_t>(1024, db->D);
   const uint32_t d_stride = (uint32_t)(db->D / n_d);
   unsigned long long *counts = ctx->d_scalars + 8;  // shared with the guess histogram: both are read back before reuse
   *launches += launch_union_sample(q_dev, nq, q_stride, db->ref, (uint32_t)db->D, d_stride, n_d, db->W, need, counts, s);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(GUESS_THREADS) union_sample_kernel(const uint6
 int launch_union_sample(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D, uint32_t d_stride,
                         uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s) {
   const uint32_t n_q = (Q + q_stride - 1) / q_stride;
-  const uint32_t per_block = 64;
+  const uint32_t per_block = 32;
   const dim3 grid((n_q + GUESS_THREADS - 1) / GUESS_THREADS, (n_d + per_block - 1) / per_block);
   cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s);
   switch (W) {

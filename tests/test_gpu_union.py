@@ -99,7 +99,7 @@ def test_union_query_matches_oracle(uctx, L):
         assert st["kernel_used"] == 2
         used.add(uctx.last_mma_k)
     assert union_k(L, uctx.degree) in used           # every mode with a bound below L ran on the union rows (forced)
-    assert len(used) == 2                            # the others (need = 0) on the single-window operands
+    assert len(used) == 2                            # the others (need < L/2) on the single-window operands
 
 
 def test_union_ties_floods_and_tiny_shapes(uctx):
