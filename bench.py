@@ -43,6 +43,8 @@ ALPHABET = "nucleotide"
 MMA_TRAFFIC = {
     192: (230.0e6 + 4.9e6, "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v8_summary.txt (algorithmic: 192 MB "
                            "db operand tiles + 19 MB query tiles, read once)"),
+    85: (163.6e6 + 6.0e6, "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v9_union3_summary.txt (algorithmic: 85 MB "
+                          "union-row db image + 26 MB query tiles; the query tile is re-fetched per db chunk, mostly from L2)"),
 }
 
 
