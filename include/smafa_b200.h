@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SMAFA_B200_ABI_VERSION 2 /* 2: smafa_stats gained guess_bound and rescanned; smafa_*_file_on_device */
+#define SMAFA_B200_ABI_VERSION 3 /* 2: smafa_stats gained guess_bound and rescanned; smafa_*_file_on_device.  3 (additive): smafa_ctx_last_mma_k, smafa_debug_mma_rate, smafa_debug_sparse_decode */
 
 typedef enum smafa_status {
   SMAFA_OK = 0,
