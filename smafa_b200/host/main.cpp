@@ -49,7 +49,35 @@ static bool parse_u32(const char *s, int64_t *out) {
   return true;
 }
 
-int main(int argc, char **argv) {
+// clap accepts `--name=value`, `-n=value` and `-nvalue` next to `--name value` (src/main.rs uses the derive defaults):
+// split those forms so the parser below only sees separate tokens.  `value_shorts` = the short options of this
+// subcommand that take a value.
+static std::vector<std::string> normalize_args(int argc, char **argv) {
+  std::vector<std::string> out;
+  std::string sub;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (sub.empty() && !a.empty() && a[0] != '-') sub = a;
+    const std::string value_shorts = sub == "query" ? "dq" : sub == "count" ? "i" : (sub.empty() ? "" : "id");
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      const size_t eq = a.find('=');
+      if (eq != std::string::npos) { out.push_back(a.substr(0, eq)); out.push_back(a.substr(eq + 1)); continue; }
+    } else if (a.size() > 2 && a[0] == '-' && a[1] != '-' && value_shorts.find(a[1]) != std::string::npos) {
+      out.push_back(a.substr(0, 2));
+      out.push_back(a.substr(a[2] == '=' ? 3 : 2));
+      continue;
+    }
+    out.push_back(a);
+  }
+  return out;
+}
+
+int main(int argc_raw, char **argv_raw) {
+  const std::vector<std::string> norm = normalize_args(argc_raw, argv_raw);
+  std::vector<char *> argv_vec{argv_raw[0]};
+  for (const std::string &a : norm) argv_vec.push_back(const_cast<char *>(a.c_str()));
+  const int argc = (int)argv_vec.size();
+  char **argv = argv_vec.data();
   int i = 1;
   auto is = [&](const char *a, const char *s, const char *l) { return (s && !strcmp(a, s)) || (l && !strcmp(a, l)); };
   while (i < argc && (is(argv[i], "-v", "--verbose") || is(argv[i], "-q", "--quiet"))) ++i;

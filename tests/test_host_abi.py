@@ -129,3 +129,21 @@ def test_limit_per_sequence_host_filter():
     n = l.smafa_apply_limit_per_sequence(hits, len(rows), db.ctypes.data, 1, 0, 1)
     got = [(hits[i].query, hits[i].subject, hits[i].distance) for i in range(n)]
     assert got == [(0, 1, 0), (0, 0, 1), (1, 1, 2)]
+
+
+def test_cli_accepts_clap_value_syntax(kat_dir, tmp_path):
+    """clap (src/main.rs:64-116) takes `--name=value`, `-n=value` and `-nvalue` as well as `--name value`."""
+    fa = kat_dir / "random_3_2.fna"
+    outs = []
+    for i, args in enumerate([["-i", fa, "-d", None], [f"--input={fa}", "--database", None], [f"-i{fa}", "-d=", None]]):
+        out = tmp_path / f"o{i}.db"
+        args = [a if a is not None else out for a in args]
+        if str(args[-2]) == "-d=":
+            args = args[:-2] + [f"-d={out}"]
+        r = cli("makedb", *args)
+        assert r.returncode == 0, r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == outs[2] == (kat_dir / "random_3_2.fna.smafadb").read_bytes()
+    r = cli("count", f"-i{fa}")
+    assert r.returncode == 0 and '"num_reads":2' in r.stdout
+    assert cli("makedb", "--input").returncode == 2
