@@ -107,6 +107,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   if (getenv("SMAFA_MMA_NSYM") != nullptr) ctx->mma_union = 1;
   if (const char *e = getenv("SMAFA_MMA_UNION")) ctx->mma_union = (e[0] >= '1' && e[0] <= '3') ? (uint32_t)(e[0] - '0') : 1u;
   if (const char *e = getenv("SMAFA_MMA_UNION_FORCE")) ctx->mma_union_force = atoi(e);
+  if (const char *e = getenv("SMAFA_DB_GROUP")) ctx->db_group = e[0] == '1';
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -251,6 +252,36 @@ static int db_add_rows(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64
   return SMAFA_OK;
 }
 
+constexpr int RC_TOO_MANY_CENTROIDS = 2;  // internal (cluster_impl)
+static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t, uint32_t *centroid_of,
+                        uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats, uint64_t max_centroids);
+
+// Similarity-grouped db order (experimental, SMAFA_DB_GROUP=1).  Union rows (scan_mma.cu) filter
+// several windows with one accumulator, and how many they can hold is set by how often the union of a row's windows
+// matches an unrelated query -- hardly more often than one window when the windows of a row are near-copies of each
+// other.  perm = the db's windows ordered by (their centroid in the library's own greedy clustering at L/4, subject):
+// families become runs of consecutive rows.  Everything on the device then works on the grouped order; candidates
+// are mapped back to subject numbers before finalize (launch_remap_subjects), so results do not change.
+// Leaves perm empty when the db has too little structure (more centroids than half its windows).
+static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm) {
+  perm.clear();
+  std::vector<uint32_t> cof(D);
+  uint64_t nc = 0;
+  const bool saved = ctx->db_group;
+  ctx->db_group = false;  // the greedy's own dbs are plain
+  int rc = cluster_impl(ctx, enc, D, L, L / 4, cof.data(), &nc, nullptr, nullptr, D / 2);
+  ctx->db_group = saved;
+  if (rc == RC_TOO_MANY_CENTROIDS) return SMAFA_OK;
+  if (rc) return rc;
+  // counting sort by centroid (centroids in input order, members in input order behind their centroid)
+  std::vector<uint32_t> start(D + 1, 0);
+  for (uint64_t i = 0; i < D; ++i) start[cof[i] + 1]++;
+  for (uint64_t i = 0; i < D; ++i) start[i + 1] += start[i];
+  perm.resize(D);
+  for (uint64_t i = 0; i < D; ++i) perm[start[cof[i]]++] = (uint32_t)i;
+  return SMAFA_OK;
+}
+
 extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset,
                                smafa_db **out) {
   if (!ctx || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: null argument");
@@ -270,6 +301,20 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
   cudaError_t e = cudaMalloc((void **)&db->invalid_flag, sizeof(int));
   if (e != cudaSuccess) { delete db; return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(db->invalid_flag, 0, sizeof(int), ctx->stream);
+  std::vector<uint64_t> grouped;
+  if (ctx->db_group && db->alphabet == ALPHA_NUC && !db->generic_only && L <= 63 && D >= 65536) {
+    int rc = group_order(ctx, enc, D, L, db->perm_host);
+    if (rc) { smafa_db_free(db); return rc; }
+    if (!db->perm_host.empty()) {
+      grouped.resize(D * db->W);
+      for (uint64_t r = 0; r < D; ++r)
+        memcpy(grouped.data() + r * db->W, enc + (uint64_t)db->perm_host[r] * db->W, db->W * sizeof(uint64_t));
+      enc = grouped.data();
+      e = cudaMalloc((void **)&db->perm, D * sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(db->perm, db->perm_host.data(), D * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { smafa_db_free(db); return fail(ctx, SMAFA_E_OOM, "grouped db order: %s", cudaGetErrorString(e)); }
+    }
+  }
   int rc = db_add_rows(ctx, db, enc, D);
   if (rc) { smafa_db_free(db); return rc; }
   *out = db;
@@ -278,6 +323,7 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
 
 extern "C" int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n) {
   if (!ctx || !db || (n && !enc)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_append: null argument");
+  if (db->perm != nullptr && n) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_append: the db is stored in grouped order (SMAFA_DB_GROUP)");
   CU(cudaSetDevice(ctx->device));
   return db_add_rows(ctx, db, enc, n);
 }
@@ -291,6 +337,7 @@ extern "C" void smafa_db_free(smafa_db *db) {
   cudaFree(db->ref);
   cudaFree(db->planes);
   cudaFree(db->invalid_flag);
+  cudaFree(db->perm);
   mma_db_free(db);
   delete db;
 }
@@ -321,6 +368,13 @@ extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_
     cudaMemcpyAsync(out + q0 * D, dout, nq * D * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "smafa_distances: %s", cudaGetErrorString(e2));
+    if (rc == SMAFA_OK && !db->perm_host.empty()) {  // grouped db: column r of the device result is subject perm[r]
+      std::vector<uint16_t> row(D);
+      for (uint64_t q = q0; q < q0 + nq; ++q) {
+        memcpy(row.data(), out + q * D, D * sizeof(uint16_t));
+        for (uint64_t r = 0; r < D; ++r) out[q * D + db->perm_host[r]] = row[r];
+      }
+    }
   }
   cudaFree(dq);
   cudaFree(dout);
@@ -425,12 +479,34 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
                                   int *launches, int *rc_out) {
   *rc_out = SMAFA_OK;
   uint32_t max_u = 1;
-  for (uint32_t u = 2; u <= 3; ++u)
-    if (db->union_img[u - 2] != nullptr) max_u = u;
+  for (uint32_t u : UNION_DEGREES)
+    if (db->union_img[union_slot(u)] != nullptr) max_u = u;
   const int need = (int)db->L - b0;
   if (max_u == 1 || 2 * need < (int)db->L) return 1;  // a union of two windows differs from a query in < L/2 positions far too often
   if (ctx->mma_union_force >= 1) return std::min<uint32_t>((uint32_t)ctx->mma_union_force, max_u);
   const double pairs = (double)nq * (double)db->D;
+  if (db->perm != nullptr && max_u > 3) {
+    // Grouped db (experimental): rows up to 16 windows wide; always sampled (such a db has >= 65536 windows).  t_u for the
+    // wider rows: a tile costs what it costs at degree 3 (MMA-bound, ~620 ns) and holds 128 u windows.
+    const uint32_t q_stride = (nq + 4095) / 4096;
+    const uint32_t n_d = (uint32_t)std::min<uint64_t>(1024, db->D);
+    const uint32_t d_stride = (uint32_t)(db->D / n_d);
+    unsigned long long *counts = ctx->d_scalars + 8;
+    *launches += launch_union_sample_wide(q_dev, nq, q_stride, db->ref, (uint32_t)db->D, d_stride, n_d, db->W, need, counts, s);
+    cudaError_t e = cudaMemcpyAsync(ctx->h_scalars + 8, counts, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { *rc_out = fail(ctx, SMAFA_E_CUDA, "union sample: %s", cudaGetErrorString(e)); return 1; }
+    const double n_s = std::max<double>(1.0, (double)ctx->h_scalars[14]);
+    static const uint32_t deg[6] = {1, 2, 3, 4, 8, 16};
+    static const double t_w[6] = {9.6e-5, 6.4e-5, 4.3e-5, 3.3e-5, 1.7e-5, 0.85e-5};
+    uint32_t best = 1;
+    double best_cost = 0;
+    for (int i = 0; i < 6 && deg[i] <= max_u; ++i) {
+      const double cost = t_w[i] + 1.5 * (double)ctx->h_scalars[8 + i] / n_s;
+      if (i == 0 || cost < best_cost) { best = deg[i]; best_cost = cost; }
+    }
+    return best;
+  }
   if (pairs < 2e9 || db->D < 65536 || nq < 1024) {
     if (max_u >= 3 && 8 * need >= 7 * (int)db->L) return 3;
     return 4 * need >= 3 * (int)db->L ? 2 : 1;
@@ -613,6 +689,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   if (st) st->candidates += n_cand;
   ctx->cand_needed = n_cand;
   if (n_cand > ctx->ws_cap) return RC_OVERFLOW;
+  if (db->perm != nullptr) launch_remap_subjects(ctx->cand, n_cand, db->perm, s);  // grouped db: rows -> subject numbers
   int fl = launch_finalize(ctx->fw, ctx->cand, n_cand, Qb, plan.k_fin, q_base, db->subject_offset, ctx->hits,
                            ctx->ws_cap, ctx->h_scalars + 1, s);
   CU(cudaStreamSynchronize(s));
@@ -809,6 +886,13 @@ extern "C" uint64_t smafa_apply_limit_per_sequence(smafa_hit *hits, uint64_t n, 
 // old centroids always have lower indices than in-batch ones), else founds a new centroid.
 extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t,
                              uint32_t *centroid_of, uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats) {
+  return cluster_impl(ctx, enc, n, L, t, centroid_of, n_centroids, n_comparisons, stats, UINT64_MAX);
+}
+
+// The greedy of src/cluster.rs:45-74.  max_centroids: give up with RC_TOO_MANY_CENTROIDS once more centroids than
+// that exist (group_order: a db without near-duplicates is not worth grouping, and its greedy would be quadratic).
+static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t, uint32_t *centroid_of,
+                        uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats, uint64_t max_centroids) {
   if (!ctx || (n && (!enc || !centroid_of))) return fail(ctx, SMAFA_E_INVALID, "smafa_cluster: null argument");
   if (stats) memset(stats, 0, sizeof *stats);
   if (n_centroids) *n_centroids = 0;
@@ -920,6 +1004,7 @@ extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, ui
       }
     }
     lap(3);
+    if (cent_input.size() > max_centroids) { rc = RC_TOO_MANY_CENTROIDS; break; }
     if (!new_words.empty()) rc = db_add_rows(ctx, cdb, new_words.data(), new_words.size() / W);
     lap(4);
     b0 += B;

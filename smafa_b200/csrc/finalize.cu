@@ -7,6 +7,7 @@
 // neighbour compare, a stable stream compaction, then conversion to smafa_hit rows.  The same
 // routine is the multi-GPU merge: the union of per-shard supersets is a superset.
 // CUB provides the sort and the compaction (library code off the hot path; the scan is ours).
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -60,6 +61,20 @@ __global__ void hits_to_keys_kernel(const smafa_hit *__restrict__ hits, uint64_t
   smafa_hit h = hits[i];
   if (h.query >= MAX_BATCH_QUERIES || h.distance > KEY_D_MASK) atomicOr(bad, 1);
   keys[i] = make_key(h.query, h.distance, h.subject);
+}
+
+// Grouped dbs (api.cu group_order): the scan ran on the db in grouped order; perm[row] is the subject number the
+// reference knows the window by.  Applied to the candidate keys before the sort, so ties come out in subject order.
+__global__ void remap_subjects_kernel(uint64_t *__restrict__ keys, uint64_t n, const uint32_t *__restrict__ perm) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    keys[i] = make_key(key_q(k), key_d(k), perm[key_j(k)]);
+  }
+}
+
+void launch_remap_subjects(uint64_t *keys, uint64_t n, const uint32_t *perm, cudaStream_t s) {
+  if (n == 0) return;
+  remap_subjects_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(keys, n, perm);
 }
 
 void launch_hits_to_keys(const smafa_hit *hits, uint64_t n, uint64_t *keys, int *bad, cudaStream_t s) {

@@ -154,6 +154,83 @@ int launch_union_sample(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, co
   return 1;
 }
 
+// The same for a grouped db (api.cu group_order), whose rows can be 1, 2, 3, 4, 8 or 16 windows wide: counts[0..5] =
+// passing (query, row) pairs of those degrees, counts[6] = samples.  The rows of degree 2, 4, 8, 16 that hold window j
+// nest inside the aligned block of 16 windows around j; the row of degree 3 is read separately.
+template <int W>
+__global__ void __launch_bounds__(GUESS_THREADS) union_sample_wide_kernel(const uint64_t *__restrict__ q_ref, uint32_t Q,
+                                                                          uint32_t q_stride, const uint64_t *__restrict__ d_ref,
+                                                                          uint32_t D, uint32_t d_stride, uint32_t n_d,
+                                                                          uint32_t per_block, int need,
+                                                                          unsigned long long *__restrict__ counts) {
+  constexpr uint64_t NBITS = 0x0084210842108421ull;
+  const uint64_t q = (uint64_t)(blockIdx.x * GUESS_THREADS + threadIdx.x) * q_stride;
+  uint64_t qw[W];
+  int nN = 0;
+#pragma unroll
+  for (int x = 0; x < W; ++x) {
+    const uint64_t v = q < Q ? q_ref[q * W + x] : 0;
+    nN += __popcll(v & NBITS);
+    qw[x] = v & ~NBITS;
+  }
+  const int thr = q < Q ? need - nN : 1 << 20;
+  uint32_t n[7] = {0, 0, 0, 0, 0, 0, 0};
+  const uint32_t i_end = min(n_d, (blockIdx.y + 1) * per_block);
+  for (uint32_t i = blockIdx.y * per_block; i < i_end; ++i) {
+    const uint32_t j = i * d_stride, b0 = j & ~15u, t0 = j / 3 * 3;
+    int c[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int x = 0; x < W; ++x) {
+      uint64_t o1 = 0, o2 = 0, o4 = 0, o8 = 0, o16 = 0;
+#pragma unroll 1
+      for (uint32_t w = 0; w < 16; ++w) {
+        const uint32_t jj = b0 + w;
+        const uint64_t v = jj < D ? d_ref[(uint64_t)jj * W + x] : 0;
+        o16 |= v;
+        if ((jj ^ j) < 8) o8 |= v;
+        if ((jj ^ j) < 4) o4 |= v;
+        if ((jj ^ j) < 2) o2 |= v;
+        if (jj == j) o1 = v;
+      }
+      uint64_t o3 = d_ref[(uint64_t)t0 * W + x];
+      if (t0 + 1 < D) o3 |= d_ref[(uint64_t)(t0 + 1) * W + x];
+      if (t0 + 2 < D) o3 |= d_ref[(uint64_t)(t0 + 2) * W + x];
+      c[0] += __popcll(qw[x] & o1);
+      c[1] += __popcll(qw[x] & o2);
+      c[2] += __popcll(qw[x] & o3);
+      c[3] += __popcll(qw[x] & o4);
+      c[4] += __popcll(qw[x] & o8);
+      c[5] += __popcll(qw[x] & o16);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) n[k] += c[k] >= thr;
+    n[6] += q < Q;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n[k] += __shfl_xor_sync(0xffffffffu, n[k], d);
+    if ((threadIdx.x & 31) == 0 && n[k]) atomicAdd(counts + k, (unsigned long long)n[k]);
+  }
+}
+
+int launch_union_sample_wide(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D,
+                             uint32_t d_stride, uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s) {
+  const uint32_t n_q = (Q + q_stride - 1) / q_stride;
+  const uint32_t per_block = 16;
+  const dim3 grid((n_q + GUESS_THREADS - 1) / GUESS_THREADS, (n_d + per_block - 1) / per_block);
+  cudaMemsetAsync(counts, 0, 7 * sizeof(unsigned long long), s);
+  switch (W) {
+    case 1: union_sample_wide_kernel<1><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 2: union_sample_wide_kernel<2><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 3: union_sample_wide_kernel<3><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 4: union_sample_wide_kernel<4><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    case 5: union_sample_wide_kernel<5><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+    default: union_sample_wide_kernel<6><<<grid, GUESS_THREADS, 0, s>>>(q_ref, Q, q_stride, d_ref, D, d_stride, n_d, per_block, need, counts); break;
+  }
+  return 1;
+}
+
 // per_query[q] = number of candidates of query q
 __global__ void count_per_query_kernel(const uint64_t *__restrict__ cand, uint64_t n, uint32_t *__restrict__ per_query) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)

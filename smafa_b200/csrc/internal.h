@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "kernels.h"
 
@@ -21,6 +22,7 @@ struct smafa_ctx {
   bool auto_prefers_mma = true;
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   uint32_t mma_union = 1;         // largest union degree dbs get operand images for (1..3 windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
+  bool db_group = false;          // SMAFA_DB_GROUP=1 (experimental, off): large nucleotide dbs are stored in similarity-grouped order (api.cu group_order)
   int mma_union_force = 0;        // SMAFA_MMA_UNION_FORCE=u: every tcgen05 scan that starts at need >= L/2 uses degree u whatever the sample says (tests)
   uint32_t mma_union_pick = 1;    // degree of the next mma_scan (set per scan by run_batch)
   uint32_t last_mma_k = 0;        // int8 contraction depth per WINDOW of the last tcgen05 scan (K / windows per row)
@@ -72,9 +74,17 @@ struct smafa_db {
   uint8_t *onehot = nullptr;
   uint32_t mma_nsym = 3;      // encoding of `onehot` (mma_pick_encoding)
   uint64_t onehot_cap = 0;
-  uint8_t *union_img[2] = {nullptr, nullptr};  // union-row images of degree 2, 3: [tiles of 128*u windows][128 rows * 4 PB bytes]
-  uint64_t union_cap[2] = {0, 0};              // in tiles
+  uint32_t *perm = nullptr;      // grouped dbs only: device row -> subject number (nullptr: rows are in subject order)
+  std::vector<uint32_t> perm_host;
+  // union-row images, one per degree of UNION_DEGREES: [tiles of 128*u windows][128 rows * 4 PB bytes]; degrees above
+  // 3 only for grouped dbs (perm != nullptr)
+  uint8_t *union_img[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t union_cap[5] = {0, 0, 0, 0, 0};     // in tiles
 };
+
+// Degrees (windows per accumulator) a union-row image can have, and the slot of a degree in smafa_db::union_img (-1: none)
+constexpr uint32_t UNION_DEGREES[5] = {2, 3, 4, 8, 16};
+inline int union_slot(uint32_t u) { return u == 2 ? 0 : u == 3 ? 1 : u == 4 ? 2 : u == 8 ? 3 : u == 16 ? 4 : -1; }
 
 const char *smafa_global_error();
 void smafa_set_global_error(const std::string &s);

@@ -57,6 +57,11 @@ size_t finalize_temp_bytes(uint64_t cap);
 int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k,
                     uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out, uint64_t hits_cap,
                     unsigned long long *n_out_pinned, cudaStream_t s);
+// the same for degrees 1, 2, 3, 4, 8, 16 (grouped dbs): counts[0..5] passing pairs, counts[6] samples
+int launch_union_sample_wide(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D,
+                             uint32_t d_stride, uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s);
+// candidate keys of a grouped db: row number -> subject number (perm on the device)
+void launch_remap_subjects(uint64_t *keys, uint64_t n, const uint32_t *perm, cudaStream_t s);
 // smafa_hit rows -> candidate keys (for the multi-GPU merge); q must be < 2^20, d < 2^12
 void launch_hits_to_keys(const smafa_hit *hits, uint64_t n, uint64_t *keys, int *bad, cudaStream_t s);
 

@@ -174,7 +174,7 @@ __device__ __forceinline__ AndTree and_tree32(const uint32_t (&v)[32]) {
 template <int KSTEPS, int NSYM, int STAGES, int EPI_WARPS, bool PACK16, int B_BUFS, bool SPLIT_N, int UPR>
 __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(const __grid_constant__ MmaParams P) {
   constexpr int MMA_EPI_WARPS = EPI_WARPS;
-  static_assert(UPR == 1 || ((UPR == 2 || UPR == 3) && NSYM == 4), "union rows need one-hot operands");
+  static_assert(UPR == 1 || ((UPR == 2 || UPR == 3 || UPR == 4 || UPR == 8 || UPR == 16) && NSYM == 4), "union rows need one-hot operands");
   constexpr uint32_t KB = KSTEPS * 32;       // operand bytes per row
   constexpr uint32_t PB = KB / NSYM;         // positions per symbol / feature block
   constexpr uint32_t BIAS_K = NSYM == (int)MMA_ENC_AA ? MMA_ENC_AA * MMA_AA_POS : PB - 1;  // one-hot: symbol A, position PB-1
@@ -424,10 +424,18 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         // a flood (bound admits > 1/4 of the chunk): verify straight from the masks, warp-wide per bit
 #pragma unroll 1
         for (int i = 0; i < 32; ++i) {
+          if constexpr (UPR <= 3) {
 #pragma unroll
-          for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
-            mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
-            if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
+            for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
+              mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
+              if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
+            }
+          } else {  // wide rows (grouped dbs): a loop, not UPR inlined copies of the verification
+#pragma unroll 1
+            for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
+              mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
+              if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
+            }
           }
         }
       } else {
@@ -443,17 +451,29 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         while (m0) {
           const int i = __ffs(m0) - 1;
           m0 &= m0 - 1;
+          if constexpr (UPR <= 3) {
 #pragma unroll
-          for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-            my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
+            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
+          } else {
+#pragma unroll 4
+            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
+          }
         }
         if constexpr (PACK16) {
           while (m1) {
             const int i = __ffs(m1) - 1;
             m1 &= m1 - 1;
+            if constexpr (UPR <= 3) {
 #pragma unroll
-            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
+              for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+                my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
+            } else {
+#pragma unroll 4
+              for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
+                my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
+            }
           }
         }
         tail += total;
@@ -796,14 +816,16 @@ static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
 // Union-row operand images (kernel template parameter UPR = 2, 3): 4-symbol one-hot, UPR windows per row.
 static uint32_t union_kb(const smafa_db *db) { return 4 * mma_pb(4, db->L); }
 static uint32_t union_max_degree(const smafa_ctx *ctx, const smafa_db *db) {
-  return (db->alphabet == ALPHA_NUC && mma_enc_ok(4, db->L)) ? std::min<uint32_t>(ctx->mma_union, 3) : 1;
+  if (db->alphabet != ALPHA_NUC || !mma_enc_ok(4, db->L)) return 1;
+  if (db->perm != nullptr && ctx->mma_union >= 3) return 16;  // grouped db: near-copies share a row, wide rows stay selective
+  return std::min<uint32_t>(ctx->mma_union, 3);
 }
 
 static int union_reserve(smafa_ctx *ctx, smafa_db *db, uint32_t upr, uint64_t rows) {
   const uint64_t per_tile = (uint64_t)upr * MMA_M;
   const uint64_t tiles = (rows + per_tile - 1) / per_tile;
-  uint8_t *&img = db->union_img[upr - 2];
-  if (tiles <= db->union_cap[upr - 2]) return SMAFA_OK;
+  uint8_t *&img = db->union_img[union_slot(upr)];
+  if (tiles <= db->union_cap[union_slot(upr)]) return SMAFA_OK;
   const size_t tile_bytes = (size_t)MMA_M * union_kb(db);
   uint8_t *n = nullptr;
   cudaError_t e = cudaMalloc((void **)&n, tiles * tile_bytes);
@@ -812,13 +834,14 @@ static int union_reserve(smafa_ctx *ctx, smafa_db *db, uint32_t upr, uint64_t ro
   cudaStreamSynchronize(ctx->stream);
   cudaFree(img);
   img = n;
-  db->union_cap[upr - 2] = tiles;
+  db->union_cap[union_slot(upr)] = tiles;
   return SMAFA_OK;
 }
 
 int mma_db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
   if (db->L == 0 || db->L > 63) return SMAFA_OK;
-  for (uint32_t upr = 2; upr <= union_max_degree(ctx, db); ++upr) {
+  for (uint32_t upr : UNION_DEGREES) {
+    if (upr > union_max_degree(ctx, db)) break;
     int rc = union_reserve(ctx, db, upr, rows);
     if (rc) return rc;
   }
@@ -844,18 +867,18 @@ int mma_db_pack(smafa_ctx *ctx, smafa_db *db, uint64_t first, uint64_t n) {
   const uint32_t padded = (end + MMA_M - 1) / MMA_M * MMA_M;
   launch_pack_operand(db->ref, end, (uint32_t)first, padded, db->W, db->L, MMA_M, mma_kb(db), db->mma_nsym, 0, 0,
                       db->alphabet, nullptr, db->onehot, ctx->stream);
-  for (uint32_t upr = 2; upr <= 3; ++upr) {  // rows that hold a window of [first, end), then the padding of the last tile
-    if (db->union_img[upr - 2] == nullptr) continue;
+  for (uint32_t upr : UNION_DEGREES) {  // rows that hold a window of [first, end), then the padding of the last tile
+    if (db->union_img[union_slot(upr)] == nullptr) continue;
     const uint32_t r_begin = (uint32_t)(first / upr), r_end = (end + upr - 1) / upr;
     launch_pack_operand(db->ref, end, r_begin, (r_end + MMA_M - 1) / MMA_M * MMA_M, db->W, db->L, MMA_M, union_kb(db), 4, 0, 0,
-                        db->alphabet, nullptr, db->union_img[upr - 2], ctx->stream, upr);
+                        db->alphabet, nullptr, db->union_img[union_slot(upr)], ctx->stream, upr);
   }
   return SMAFA_OK;
 }
 
 void mma_db_free(smafa_db *db) {
   cudaFree(db->onehot);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 5; ++i) {
     cudaFree(db->union_img[i]);
     db->union_img[i] = nullptr;
     db->union_cap[i] = 0;
@@ -880,7 +903,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   // Operand choice for this scan: ctx->mma_union_pick windows per db operand row (api.cu pick_union_degree), if this
   // db holds that image; the db's own encoding (+-1 features by default) with one window per row otherwise.
   uint32_t upr = ctx->mma_union_pick;
-  if (upr < 2 || upr > 3 || db->union_img[upr - 2] == nullptr) upr = 1;
+  if (union_slot(upr) < 0 || db->union_img[union_slot(upr)] == nullptr) upr = 1;
   const bool use_union = upr > 1;
   const uint32_t enc = use_union ? 4u : db->mma_nsym;
   const uint32_t KB = use_union ? union_kb(db) : mma_kb(db);
@@ -905,7 +928,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
                       ctx->q_onehot, s);
   P.dump = dump;
   P.q_meta = meta;
-  P.a_tiles = use_union ? db->union_img[upr - 2] : db->onehot;
+  P.a_tiles = use_union ? db->union_img[union_slot(upr)] : db->onehot;
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
   P.n_db_tiles = (uint32_t)((db->D + MMA_M * upr - 1) / (MMA_M * upr));
@@ -930,13 +953,18 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   if (use_union) {
     // SMAFA_MMA_UNION_STAGES4=1 (ablation): one query operand buffer and four db tile stages instead of two and two
     static const bool stages4 = getenv("SMAFA_MMA_UNION_STAGES4") ? atoi(getenv("SMAFA_MMA_UNION_STAGES4")) != 0 : false;
-    if (stages4 && wide) {
+    if (stages4 && wide && upr <= 3) {
       e = upr == 2 ? launch_mma<8, 4, 4, 8, true, 1, false, 2>(P, grid, s) : launch_mma<8, 4, 4, 8, true, 1, false, 3>(P, grid, s);
       if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
       return 2;
     }
-    if (upr == 2) e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s);
-    else e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 3>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 3>(P, grid, s);
+    switch (upr) {
+      case 2: e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 2>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 2>(P, grid, s); break;
+      case 3: e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 3>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 3>(P, grid, s); break;
+      case 4: e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 4>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 4>(P, grid, s); break;
+      case 8: e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 8>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 8>(P, grid, s); break;
+      default: e = wide ? launch_mma<8, 4, 2, 8, true, 2, false, 16>(P, grid, s) : launch_mma<4, 4, 4, 8, true, 2, false, 16>(P, grid, s); break;
+    }
     if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
     return 2;
   }
