@@ -212,7 +212,10 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
                 "traffic_source": MMA_TRAFFIC.get(mma_k, (None, "no ncu capture for these operands"))[1],
                 "operands": {192: "+-1 character features, one window per accumulator (K = 192)",
                              128: "one-hot union rows, two windows per accumulator (K = 256 per row)",
-                             85: "one-hot union rows, three windows per accumulator (K = 256 per row)"}.get(
+                             85: "one-hot union rows, three windows per accumulator (K = 256 per row)",
+                             64: "one-hot union rows, four windows per accumulator (grouped db)",
+                             32: "one-hot union rows, eight windows per accumulator (grouped db)",
+                             16: "one-hot union rows, sixteen windows per accumulator (grouped db)"}.get(
                                  mma_k, f"K = {mma_k} per window")}
     # POPC formulation: the binding unit is the POPC pipe.  Reference layout = 10 x (XOR32+POPC32)
     # per comparison (5 u64 words, src/lib.rs:85).  The bit-plane packing needs 2 (1 with early exit).

@@ -3,12 +3,13 @@
 // Replaces WindowSet::get_distances + the first selection stage (reference src/lib.rs:71-89,
 // 243-265, 298-312).
 //
-// Operands (int8, K-major, UMMA canonical no-swizzle layout = 8-row x 16-byte core matrices):
+// The literal formulation (ENC = 5), which the other operand encodings below refine:
+//   Operands (int8, K-major, UMMA canonical no-swizzle layout = 8-row x 16-byte core matrices):
 //   K index = symbol * PB + position, symbol in {A,C,G,T,N}, PB = 64 (L <= 63) or 32 (L <= 31)
 //   => K = 320 (10 MMA k-steps of 32) or 160 (5 k-steps).
-//   A = db tile, M = 128 windows (TMEM lanes), streamed: one contiguous 40 KB image per tile in
-//       global memory, fetched with a single cp.async.bulk (TMA bulk copy, no tensor map needed
-//       because pack_onehot_kernel already writes the shared-memory image).
+//   A = db tile, M = 128 operand rows (TMEM lanes), streamed: one contiguous image per tile in global memory,
+//       fetched with a single cp.async.bulk (TMA bulk copy, no tensor map needed because pack_operand_kernel
+//       already writes the shared-memory image).
 //   B = query tile, N = 256 queries (TMEM columns), resident in shared memory for a whole work item.
 //   D = A.B^T in TMEM, int32, two 256-column buffers (MMA of tile t+1 overlaps the drain of tile t).
 // Threshold folded into the MMA: the spare K slot (symbol A, position PB-1) holds 1 in every db row
@@ -19,12 +20,15 @@
 // is a conservative filter and bit-exactness never depends on it.  The bias bytes are refreshed from
 // the global bounds every tile by the otherwise idle producer warp (stale = looser = still a
 // superset).
+// What runs by default: +-1 character-feature operands (ENC = 3, K = 192, one window per
+// row) when the bound is loose; one-hot union rows (ENC = 4, K = 256, UPR = 2 or 3 windows per row, i.e. per
+// accumulator) when it is tight -- the caller picks per scan (api.cu pick_union_degree).
 //
 // Warp roles (448 threads, 1 CTA/SM, persistent over work items = query tile x db chunk):
-//   warp 0 : bulk-copy producer (B once per item, A tiles through a 3-stage mbarrier ring) + bias refresh
+//   warp 0 : bulk-copy producer (B once per item, A tiles through a 2..4-stage mbarrier ring) + bias refresh
 //   warp 1 : TMEM allocation, single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-9 : epilogue, two warps per TMEM lane quarter (128 columns each, tcgen05.ld 32x32b.x32); survivors of the
-//               sign filter go to a per-warp shared-memory ring
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter (128 columns each, tcgen05.ld 32x32b.x32.pack::16b); survivors
+//               of the sign filter go to a per-warp shared-memory ring as (query, window) pairs
 //   warps 10-13 : verifiers, drain the rings (exact distance, candidate emission, bound tightening)
 #include <algorithm>
 #include <cstdlib>
