@@ -108,6 +108,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   if (const char *e = getenv("SMAFA_MMA_UNION")) ctx->mma_union = (e[0] >= '1' && e[0] <= '3') ? (uint32_t)(e[0] - '0') : 1u;
   if (const char *e = getenv("SMAFA_MMA_UNION_FORCE")) ctx->mma_union_force = atoi(e);
   if (const char *e = getenv("SMAFA_DB_GROUP")) ctx->db_group = e[0] == '1';
+  if (const char *e = getenv("SMAFA_UNION_VERIFY_NS")) { const double v = atof(e); if (v > 0) ctx->union_verify_ns = v; }
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
@@ -502,7 +503,7 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
     uint32_t best = 1;
     double best_cost = 0;
     for (int i = 0; i < 6 && deg[i] <= max_u; ++i) {
-      const double cost = t_w[i] + 1.5 * (double)ctx->h_scalars[8 + i] / n_s;
+      const double cost = t_w[i] + ctx->union_verify_ns * (double)ctx->h_scalars[8 + i] / n_s;
       if (i == 0 || cost < best_cost) { best = deg[i]; best_cost = cost; }
     }
     return best;
@@ -526,7 +527,7 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
   uint32_t best = 1;
   double best_cost = 0;
   for (uint32_t u = 1; u <= max_u; ++u) {
-    const double cost = t_u[u - 1] + 1.5 * (double)ctx->h_scalars[8 + u - 1] / n_s;
+    const double cost = t_u[u - 1] + ctx->union_verify_ns * (double)ctx->h_scalars[8 + u - 1] / n_s;
     if (u == 1 || cost < best_cost) { best = u; best_cost = cost; }
   }
   return best;

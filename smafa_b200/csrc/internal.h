@@ -22,6 +22,7 @@ struct smafa_ctx {
   bool auto_prefers_mma = true;
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   uint32_t mma_union = 1;         // largest union degree dbs get operand images for (1..3 windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
+  double union_verify_ns = 1.5;   // cost of one verified window in pick_union_degree's model; SMAFA_UNION_VERIFY_NS (calibration)
   bool db_group = false;          // SMAFA_DB_GROUP=1 (experimental, off): large nucleotide dbs are stored in similarity-grouped order (api.cu group_order)
   int mma_union_force = 0;        // SMAFA_MMA_UNION_FORCE=u: every tcgen05 scan that starts at need >= L/2 uses degree u whatever the sample says (tests)
   uint32_t mma_union_pick = 1;    // degree of the next mma_scan (set per scan by run_batch)
