@@ -8,13 +8,15 @@
 One "step" = one pass of the hot path over one batch of synthetic input: every query of the
 batch against every db window, max-divergence filter and best-hit selection included, producing
 the final hit rows.  Workload at N=1 = BASELINE.json configs[1]: 100k queries x 1M windows, 60 nt,
---max-divergence 5 (Mode A).  At N>1 the db is row-sharded with a fixed 1M-window shard per GPU
-(weak scaling; N=8 is the 8M-window analogue of configs[2]) and the per-shard candidates are merged
-with an NCCL all-gather every step.
+--max-divergence 5 (Mode A).  At N>1 ONE db of N x 1M windows is generated (same generator, same seed), row-sharded
+into contiguous ranges (1M-window shard per GPU: weak scaling) and the queries are drawn from the whole db, so every
+shard holds hits of every query batch; the per-shard answers are exchanged with one ncclAllGather and merged inside
+the library every step.  `--db-per-gpu 1250000 --queries 1000000` at N=8 is BASELINE.json configs[2] (1M x 10M).
 
-`value`     : comparisons/s with queries and db resident in HBM (smafa_query_dev + merge).
-`e2e`       : the same through the host-facing call (pinned host queries in, host hit rows out;
-              H2D and D2H inside the timed region).
+`value`     : comparisons/s with queries and db resident in HBM (smafa_query_sharded_dev; smafa_query_dev at N=1).
+`e2e`       : the same through the host-facing C-ABI call (smafa_query_sharded / smafa_query: pinned host queries
+              in, host hit rows out; H2D, scan, exchange, merge and D2H inside the timed region).
+At every N rank 0 checks the GPU rows of a query sample against the oracle on the WHOLE db (`cpu_baseline.matches_gpu_rows`).
 `roofline`  : for the scan kernel, from CUDA events around it (smafa_stats.scan_ms).
 `cpu_baseline`: the oracle (a port of the reference's algorithm; the Rust reference cannot be built
               in this image) timed on the host cores on a bounded query sample.
@@ -39,7 +41,8 @@ MAX_DIVERGENCE = 5
 ALPHABET = "nucleotide"
 # dram__bytes_read.sum + dram__bytes_write.sum of one scan_mma_kernel launch at the default workload (ncu --set full),
 # keyed by the contraction depth per window of the operands that ran (192: +-1 feature operands, one window per row;
-# 85: one-hot union rows, three windows per accumulator).  Other operand choices have no capture: traffic = null.
+# 85: one-hot union rows, three windows per accumulator).  A CONSTANT from the named capture, not re-measured per run
+# (ncu cannot run inside a timed bench); other operand choices have no capture: traffic = null.
 MMA_TRAFFIC = {
     192: (230.0e6 + 4.9e6, "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v8_summary.txt (algorithmic: 192 MB "
                            "db operand tiles + 19 MB query tiles, read once)"),
@@ -86,18 +89,26 @@ def workload_name(a, n):
 
 
 def make_inputs(a, rank, n):
+    """ONE db of n x db_per_gpu windows (the SURVEY 8d generator, one seed), queries drawn from the whole of it.
+    Returns (this rank's shard as words, query words, first global row of the shard, whole db as symbols)."""
     from smafa_b200 import synth
-    # every rank derives its own shard from a rank-specific seed; queries come from shard 0's
-    # generator state so they are identical on every rank
+    from smafa_b200.dist import shard_bounds
+    D = a.db_per_gpu * n
     if a.alphabet == "protein":
-        db0 = synth.make_db_aa(a.db_per_gpu, L=L, seed=synth.SEED_PROTEIN)
-        q_sym = synth.make_queries_aa(db0, a.queries, seed=synth.SEED_PROTEIN + 1)
-        shard = db0 if rank == 0 else synth.make_db_aa(a.db_per_gpu, L=L, seed=synth.SEED_PROTEIN + 7919 * rank)
-        return synth.pack_symbols_aa(shard), synth.pack_symbols_aa(q_sym)
-    db0 = synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB)
-    q_sym = synth.make_queries(db0, a.queries, seed=synth.SEED_QUERY)
-    shard = db0 if rank == 0 else synth.make_db(a.db_per_gpu, L=L, seed=synth.SEED_DB + 7919 * rank)
-    return synth.pack_symbols(shard), synth.pack_symbols(q_sym)
+        db_sym = synth.make_db_aa(D, L=L, seed=synth.SEED_PROTEIN)
+        q_sym = synth.make_queries_aa(db_sym, a.queries, seed=synth.SEED_PROTEIN + 1)
+        pack = synth.pack_symbols_aa
+    else:
+        db_sym = synth.make_db(D, L=L, seed=synth.SEED_DB)
+        q_sym = synth.make_queries(db_sym, a.queries, seed=synth.SEED_QUERY)
+        pack = synth.pack_symbols
+    lo, hi = shard_bounds(D, n, rank)
+    return pack(db_sym[lo:hi]), pack(q_sym), lo, db_sym
+
+
+def pack_db(db_sym):
+    from smafa_b200 import synth
+    return (synth.pack_symbols_aa if ALPHABET == "protein" else synth.pack_symbols)(db_sym)
 
 
 class ClockSampler:
@@ -192,23 +203,25 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
     are reused Q x D times, compulsory HBM traffic is a few hundred MB per step."""
     secs = scan_ms / 1e3
     if kernel_used == 2:
-        # Algorithmic work (SURVEY.md 8d): one-hot(query) . one-hot(db)^T over 5 symbols x L = 2*5*L int8 ops per
-        # comparison.  The kernel contracts over denser operands (+-1 character features of the 2-bit base code,
-        # K = 192 per window; or one-hot union rows, two windows per accumulator, K = 128 per window), so it
-        # EXECUTES 2*mma_k ops per comparison: `frac` (algorithmic, the contract's definition) can exceed 1;
-        # `frac_executed` is the tensor-pipe utilisation.
+        # `frac` = EXECUTED int8 ops / s over the int8 tensor peak: the tensor-pipe utilisation (<= 1).  The kernel
+        # executes 2 * mma_k ops per comparison (mma_k = contraction depth per window of the operands that ran: +-1
+        # character features K = 192, or one-hot union rows K = 256 shared by 2 or 3 windows).  SURVEY.md 8d's
+        # ALGORITHMIC figure -- one-hot(query) . one-hot(db)^T over 5 symbols x L = 2*5*L ops per comparison -- is
+        # reported next to it as `frac_algorithmic`; it exceeds 1 because the union-row filter does 3.5x less tensor
+        # work per comparison than that formulation, which is an algorithmic saving, not a utilisation.
         ops = 2 * (5 if ALPHABET == "nucleotide" else 23) * L  # one-hot symbols x positions
-        achieved = pairs_per_launch * ops / secs / 1e12
+        algorithmic = pairs_per_launch * ops / secs / 1e12
         executed = pairs_per_launch * 2 * mma_k / secs / 1e12
-        # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's
-        # issue-only tcgen05 kind::i8 probe (smafa_debug_mma_peak) on this GPU, same clocks.
-        return {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s",
+        # MEASURED_PEAKS.json only has bf16; the int8 dense rate is measured live by the library's issue-only tcgen05
+        # kind::i8 probe (smafa_debug_mma_peak) on this GPU at the same clocks, and cross-checked once against the
+        # theoretical rate (148 SMs x 16384 int8 ops/clk x SM clock) and cuBLASLt IGEMM (profiles/r02_int8_peak_crosscheck.txt).
+        return {"bound": "tensor", "achieved": executed, "peak": int8_peak, "unit": "TFLOP/s",
                 "unit_note": "integer path: 1 'FLOP' here = one int8 multiply or add on the tensor pipe (TOP/s)",
-                "frac": achieved / int8_peak, "traffic": MMA_TRAFFIC.get(mma_k, (None, None))[0],
+                "frac": executed / int8_peak, "traffic": MMA_TRAFFIC.get(mma_k, (None, None))[0],
                 "peak_source": "measured in this run: tcgen05.mma kind::i8 M128xN256xK32 issue-only probe "
                                f"on all SMs; for reference 2 x {peaks_kind} bf16_tflops = {2 * peaks['bf16_tflops']:.0f}",
-                "ops_per_comparison": ops, "executed_ops_per_comparison": 2 * mma_k,
-                "achieved_executed": executed, "frac_executed": executed / int8_peak,
+                "executed_ops_per_comparison": 2 * mma_k, "algorithmic_ops_per_comparison": ops,
+                "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / int8_peak,
                 "traffic_source": MMA_TRAFFIC.get(mma_k, (None, "no ncu capture for these operands"))[1],
                 "operands": {192: "+-1 character features, one window per accumulator (K = 192)",
                              128: "one-hot union rows, two windows per accumulator (K = 256 per row)",
@@ -229,14 +242,18 @@ def roofline(kernel_used, pairs_per_launch, scan_ms, peaks, peaks_kind, clocks, 
                            "binding unit of the bit-plane formulation (1 POPC + 2 LOP3 per pair); on the reference "
                            "word layout the same comparison costs 10 POPC",
             "ops_per_comparison": popc_per_cmp, "reference_layout_popc_per_comparison": 10,
-            "traffic_source": "ncu dram__bytes, profiles/r01_ncu_popc_early_summary.txt"}
+            "traffic_source": "constant from ncu dram__bytes, profiles/r01_ncu_popc_early_summary.txt"}
 
 
 def run_reference(a):
+    """The reference arm: the oracle port of the reference's algorithm on all host threads (the Rust reference cannot
+    be built in this image), same workload as the B200 arm at this N, each step a bounded query sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    db, q = make_inputs(a, 0, 1)
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(a.gpus))), a.gpus)
+    _, q, _, db_sym = make_inputs(a, 0, world)
+    db = pack_db(db_sym)
     mode_k = None if a.mode == "a" else 10
     times, cb = [], None
     per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(1, a.steps + a.warmup)))
@@ -252,7 +269,7 @@ def run_reference(a):
         "impl": "reference", "metric": "pairwise window comparisons/sec", "value": value, "unit": "comparisons/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / max(1, len(times)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64-popcount",
-        "data": "synthetic", "config": {"workload": workload_name(a, 1), "sampled": cb["sample"]},
+        "data": "synthetic", "config": {"workload": workload_name(a, world)},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -279,17 +296,23 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # torch.distributed carries the barrier, the max-over-ranks of the timings and the one-time broadcast of the
+        # library's communicator id; the per-step exchange is the library's own ncclAllGather (csrc/sharded.cu)
         dist.init_process_group("nccl", device_id=dev)
 
-    db, q = make_inputs(a, rank, world)
+    shard, q, shard_lo, db_sym = make_inputs(a, rank, world)
+    D_total = db_sym.shape[0]
+    if rank != 0 or a.no_cpu_baseline:
+        db_sym = None  # only rank 0 needs the whole db again (oracle check)
     ctx = smafa_b200.Context(local_rank, a.kernel)
     ctx.set_alphabet(a.alphabet)
-    searcher = ShardedSearcher(ctx, db, L, world_size=world, rank=rank, presharded=True)
+    searcher = ShardedSearcher(ctx, shard, L, world_size=world, rank=rank, presharded=True, shard_offset=shard_lo,
+                               total_rows=D_total)
     mode_k = None if a.mode == "a" else 10
     q_pinned = torch.from_numpy(q.view(np.int64)).pin_memory()
     q_dev = q_pinned.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pairs_per_step = a.queries * a.db_per_gpu * world
+    pairs_per_step = a.queries * D_total
 
     def barrier():
         if world > 1:
@@ -329,7 +352,7 @@ def main():
     ms_total = float(t.item())
     value = pairs_per_step * a.steps / (ms_total / 1e3)
 
-    # ---- end to end through the host-facing call ----
+    # ---- end to end through the host-facing C-ABI call ----
     for _ in range(2):
         host_rows = searcher.query_host(q_pinned, MAX_DIVERGENCE, mode_k)
     barrier()
@@ -342,6 +365,14 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pairs_per_step * a.steps / float(te.item())
     assert host_rows.shape[0] == n_rows
+    # every rank holds the complete answer: they must agree bit for bit
+    same_everywhere = True
+    if world > 1:
+        digest = torch.tensor([int(host_rows.astype(np.uint64).sum() % (1 << 62)), host_rows.shape[0]], dtype=torch.int64, device=dev)
+        lo_d, hi_d = digest.clone(), digest.clone()
+        dist.all_reduce(lo_d, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_d, op=dist.ReduceOp.MAX)
+        same_everywhere = bool((lo_d == hi_d).all().item())
 
     if rank == 0:
         peaks, peaks_kind = load_peaks()
@@ -358,21 +389,31 @@ def main():
             "config": {"workload": workload_name(a, world), "kernel": {1: "popc", 2: "mma", 0: "generic"}[st["kernel_used"]],
                        "l2": "flushed between timed steps (256 MiB write)", "hit_rows": int(n_rows),
                        "candidates_per_step": int(st["candidates"]), "parallelism": f"db-row-shard x{world}",
+                       "db": f"one {D_total}-window db (seed {0x5AFA0001:#x}), contiguous row shards, queries drawn from the whole db",
+                       "rows_identical_on_all_ranks": same_everywhere,
                        # selection without a useful bound scans under a guessed bound first (csrc/guess.cu)
                        "guess_bound": int(st["guess_bound"]), "rescanned_queries": int(st["rescanned"])},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "comparisons/s",
-                    "h2d_bytes_per_step": int(q.nbytes) * world, "d2h_bytes_per_step": int(host_rows.nbytes)},
+                    "h2d_bytes_per_step": int(q.nbytes) * world, "d2h_bytes_per_step": int(host_rows.nbytes) * world,
+                    "entry_point": "smafa_query_sharded (C ABI, host buffers)" if world > 1 else "smafa_query (C ABI, host buffers)"},
+            # kernels of this rank per timed region as the library counts them (smafa_stats.kernel_launches: its own
+            # launches plus CUB's radix-sort / select kernels; NCCL's all-gather kernel counts as one)
             "gpu_launches": int(launches),
             "roofline": roof,
             "scan_ms_per_step": scan_ms / a.steps, "wall_s_timed_region": t_wall,
         }
-        if world == 1 and not a.no_cpu_baseline:
-            cb, cpu_hits, n = cpu_baseline(db, q, a.cpu_seconds, mode_k)
+        if not a.no_cpu_baseline:
+            # rank 0: the oracle on a bounded prefix of the same queries against the WHOLE db -- the timing is the CPU
+            # baseline, the rows are the parity check of the sharded scan + exchange + merge at this N
+            cb, cpu_hits, n = cpu_baseline(pack_db(db_sym), q, a.cpu_seconds if world == 1 else min(a.cpu_seconds, 8.0), mode_k)
             got = host_rows[host_rows[:, 0] < n]
-            cb["matches_gpu_rows"] = bool(got.shape == cpu_hits.shape and (got == cpu_hits).all())
+            cb["matches_gpu_rows"] = bool(got.shape == cpu_hits.shape and (got == cpu_hits).all()) and same_everywhere
+            cb["checked_queries"] = int(n)
             out["cpu_baseline"] = cb
         print(json.dumps(out))
+    if world > 1:
+        dist.barrier()  # the other ranks wait for rank 0's oracle check before the process group goes away
     searcher.close()
     ctx.close()
     if world > 1:

@@ -19,8 +19,10 @@
  *  - Return value: SMAFA_OK (0) or a negative smafa_status.  No C++ exception crosses the ABI.
  *    smafa_last_error() gives a message; for the three statuses that model reference panics
  *    it is the reference's panic text.
- *  - A context is single-owner, not re-entrant (the reference is single-threaded).  One context
- *    drives one GPU; multi-GPU runs use one process per GPU (see smafa_b200/dist.py).
+ *  - A context is single-owner, not re-entrant (the reference is single-threaded).  A context made by
+ *    smafa_ctx_create drives one GPU; smafa_ctx_create_multi makes one that row-shards every db over several GPUs
+ *    of this process and is used through the same calls.  Launchers that start one process per GPU (torchrun, MPI)
+ *    use smafa_ctx_comm_init + smafa_db_upload_shard + smafa_query_sharded instead.
  *  - There is no CPU fallback: without a usable sm_100 device every compute entry point
  *    returns SMAFA_E_CUDA.
  */
@@ -34,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SMAFA_B200_ABI_VERSION 3 /* 2: smafa_stats gained guess_bound and rescanned; smafa_*_file_on_device.  3 (additive): smafa_ctx_last_mma_k, smafa_debug_mma_rate, smafa_debug_sparse_decode */
+#define SMAFA_B200_ABI_VERSION 4 /* 2: smafa_stats gained guess_bound and rescanned; smafa_*_file_on_device.  3 (additive): smafa_ctx_last_mma_k.  4: multi-GPU entry points (smafa_ctx_create_multi, smafa_ctx_comm_init, smafa_db_upload_shard, smafa_query_sharded[_dev], smafa_*_file_on_devices); the round-1 probe hooks smafa_debug_mma_rate / smafa_debug_sparse_decode are gone */
 
 typedef enum smafa_status {
   SMAFA_OK = 0,
@@ -46,6 +48,8 @@ typedef enum smafa_status {
   SMAFA_E_OOM = -11,
   SMAFA_E_INVALID = -12,     /* bad argument (null pointer, L == 0 with D > 0, ...) */
   SMAFA_E_UNSUPPORTED = -13, /* L > 4095 or D >= 2^32 */
+  SMAFA_E_NCCL = -14,        /* NCCL unavailable or a collective failed (one-process-per-GPU runs only) */
+  SMAFA_E_PEER = -15,        /* another rank of a sharded query failed; its status is in the message */
   SMAFA_E_IO = -20,          /* host file API: Err(..) in the reference (exit code 1) */
   SMAFA_E_PANIC = -21        /* host file API: any other reference panic (exit code 101) */
 } smafa_status;
@@ -89,6 +93,9 @@ typedef struct smafa_stats {
   float total_ms;          /* device time of the whole call */
   int32_t guess_bound;     /* bound of the optimistic first pass of the last batch (-1: none; csrc/guess.cu) */
   uint32_t rescanned;      /* queries the first pass left unfinished (scanned again under the caller's bound) */
+  float exchange_ms;       /* sharded queries: device time from the end of this shard's local part to the end of the
+                              merge (block exchange + merge + the wait for the slowest shard); 0 otherwise */
+  uint32_t union_degree;   /* db windows per accumulator of the last tcgen05 scan (1 = single-window operands; 0 = no such scan) */
 } smafa_stats;
 
 int smafa_abi_version(void);
@@ -100,6 +107,14 @@ void smafa_ctx_destroy(smafa_ctx *ctx);
 /* Message for the last failure on this context (or the last failure of ctx-less calls when
  * ctx == NULL).  Never NULL. */
 const char *smafa_last_error(const smafa_ctx *ctx);
+/* One context over several GPUs of this process: smafa_db_upload row-shards the db into contiguous
+ * ranges, one per device (global subject numbers are kept, so print order survives), smafa_query / smafa_query_file
+ * scan all shards concurrently (one host thread per device), move every shard's answer to the first device over
+ * NVLink and merge there (csrc/merge.cu).  smafa_cluster's greedy is strictly sequential (src/cluster.rs:45-74) and
+ * runs on the first device.  Device pointers belong to one device: the *_dev calls refuse such a context.
+ * n_devices == 1 is exactly smafa_ctx_create. */
+int smafa_ctx_create_multi(smafa_ctx **ctx, const int *devices, int n_devices, int kernel /* smafa_kernel */);
+int smafa_ctx_device_count(const smafa_ctx *ctx);
 int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel);
 /* Alphabet of the dbs uploaded from now on (a db keeps the alphabet it was uploaded with; queries are
  * read in their db's alphabet), of smafa_cluster input and of the *_file calls on this context. */
@@ -153,6 +168,31 @@ int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc_de
 int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n, int64_t max_divergence,
                     int64_t max_num_hits, uint64_t *n_out, void *stream);
 
+/* ---- sharded query, one process per GPU ------------------------------------
+ * Every rank holds a context on its GPU and one contiguous row range of the db; queries are replicated.  A call is
+ * COLLECTIVE: every rank makes it with the same queries and parameters, every rank receives the complete answer
+ * (identical rows, print order, global subject numbers).  Per <= 2^20 queries: local scan + selection, ONE
+ * ncclAllGather of fixed-capacity blocks on the call's stream, a sort-free merge (csrc/merge.cu), one host
+ * read-back.  A rank whose local part fails still joins the exchange, so all ranks return (the others with
+ * SMAFA_E_PEER).  NCCL is loaded at run time (libnccl.so.2); nothing else in this header needs it.
+ *   rank 0:  smafa_comm_unique_id(id);   broadcast id by whatever means the launcher has (a file, MPI, torch.distributed)
+ *   all:     smafa_ctx_comm_init(ctx, id, rank, world_size);
+ *            smafa_db_upload_shard(ctx, rows [lo, hi) of the db, hi - lo, L, lo, D_total, &db);
+ *            smafa_query_sharded(ctx, db, queries, ...);            (or _dev: device pointers in and out) */
+#define SMAFA_COMM_ID_BYTES 128
+int smafa_comm_unique_id(uint8_t *id /* [SMAFA_COMM_ID_BYTES] */);
+int smafa_ctx_comm_init(smafa_ctx *ctx, const uint8_t *id /* [SMAFA_COMM_ID_BYTES] */, int rank, int world_size);
+void smafa_ctx_comm_free(smafa_ctx *ctx);
+int smafa_db_upload_shard(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)]: this shard's rows */, uint64_t D,
+                          uint32_t L, uint64_t subject_offset /* first global row of the shard */,
+                          uint64_t D_total /* rows of the whole db */, smafa_db **db);
+int smafa_query_sharded(smafa_ctx *ctx, const smafa_db *db_shard, const uint64_t *q_enc, uint64_t Q, uint32_t q_len,
+                        int64_t max_divergence, int64_t max_num_hits, smafa_hit **hits, uint64_t *n_hits,
+                        smafa_stats *stats);
+int smafa_query_sharded_dev(smafa_ctx *ctx, const smafa_db *db_shard, const uint64_t *q_enc_dev, uint64_t Q,
+                            uint32_t q_len, int64_t max_divergence, int64_t max_num_hits, smafa_hit *hits_dev,
+                            uint64_t hits_capacity, uint64_t *n_hits, void *stream, smafa_stats *stats);
+
 /* --limit-per-sequence (src/lib.rs:259-260,269-289): run-length cap over consecutive hits of
  * one query whose subjects have identical encodings.  In-place on a host array; returns the
  * new length.  db_enc is the host copy of the db words ([D][W]). */
@@ -196,6 +236,13 @@ int smafa_query_file_on_device(int device, int kernel, int alphabet, const char 
                                int out_fd, smafa_ctx **ctx_out);
 int smafa_cluster_file_on_device(int device, int kernel, int alphabet, const char *input_fasta,
                                  uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out);
+/* The same over a list of GPUs (the CLI's --devices): `query` runs on a multi-device context (smafa_ctx_create_multi:
+ * db row-sharded over the devices); `cluster` is sequential by definition and uses the first device only. */
+int smafa_query_file_on_devices(const int *devices, int n_devices, int kernel, int alphabet, const char *db_path,
+                                const char *query_fasta, int64_t max_divergence, int64_t max_num_hits,
+                                int64_t limit_per_sequence, int out_fd, smafa_ctx **ctx_out);
+int smafa_cluster_file_on_devices(const int *devices, int n_devices, int kernel, int alphabet, const char *input_fasta,
+                                  uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out);
 int smafa_count_files(const char *const *paths, size_t n_paths, int out_fd);
 /* Loads a db file into host words (src/lib.rs:206-218: File::open, version gate, postcard decode) -- the
  * LEB128 stream is decoded on all host threads.  *words ([n][W], reference bit layout) is released with
@@ -222,15 +269,6 @@ int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_e
 /* Measured dense int8 tcgen05 rate of this GPU in TOP/s (roofline denominator of the MMA kernel):
  * every SM issues mmas_per_cta back-to-back M128 x N256 x K32 kind::i8 MMAs on resident operands. */
 int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops);
-/* Issue rate of other instruction shapes a scan could use, in ns per k-step and SM (csrc/probe.cu):
- * shape 0 = dense M128 x N256 x K32 (the shape the scan issues), 1 = the same k-step as two N = 128 instructions,
- * 2 = 2:4-sparse kind::i8 M128 x N256 x K64 (tcgen05.mma.sp; a one-hot window operand is a legal sparse A). */
-int smafa_debug_mma_rate(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step);
-/* What the tensor core reconstructs from (compressed A, sparsity metadata): out[s][m][k] = logical A element k of
- * row m in step s (B is the identity).  a_comp [128][64] int8 (32 per step), meta [128][4] u32 (2 per step),
- * n_steps 1 or 2, meta_path 0 = tcgen05.st, 1 = tcgen05.cp.128x128b from 16-byte shared-memory rows. */
-int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path,
-                              int32_t *out /* [n_steps][128][64] */);
 /* Contraction depth K (int8 elements per window) of the tcgen05 operands of this db, 0 if the db is
  * not eligible for the MMA kernel: executed int8 ops per comparison = 2 * K. */
 uint32_t smafa_db_mma_k(const smafa_db *db);

@@ -14,6 +14,8 @@ CLI_PATH = os.path.join(_HERE, "bin", "smafa")
 KERNEL_AUTO, KERNEL_POPC, KERNEL_MMA = 0, 1, 2
 _KERNELS = {"auto": 0, "popc": 1, "mma": 2}
 
+COMM_ID_BYTES = 128
+
 # status codes that model reference panics (process exit 101)
 _PANIC_CODES = {-1, -2, -3, -4, -21}
 
@@ -29,6 +31,14 @@ class SmafaPanic(SmafaError):
     """The reference would have panicked (exit code 101) with this message."""
 
 
+class SmafaCapacityError(SmafaError):
+    """A caller-provided device buffer is too small; .needed = rows the answer has."""
+
+    def __init__(self, needed, message):
+        super().__init__("SMAFA_E_OOM", message)
+        self.needed = needed
+
+
 class Hit(C.Structure):
     _fields_ = [("query", C.c_uint32), ("subject", C.c_uint32), ("distance", C.c_uint32)]
 
@@ -36,7 +46,8 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("candidates", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("retries", C.c_uint32), ("kernel_used", C.c_uint32), ("scan_ms", C.c_float),
-                ("total_ms", C.c_float), ("guess_bound", C.c_int32), ("rescanned", C.c_uint32)]
+                ("total_ms", C.c_float), ("guess_bound", C.c_int32), ("rescanned", C.c_uint32),
+                ("exchange_ms", C.c_float), ("union_degree", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -99,8 +110,16 @@ def load_library():
     l.smafa_debug_mma_peak.argtypes = [vp, u32, C.POINTER(C.c_double)]
     l.smafa_ctx_last_mma_k.argtypes = [vp]
     l.smafa_ctx_last_mma_k.restype = u32
-    l.smafa_debug_mma_rate.argtypes = [vp, C.c_int, u32, C.POINTER(C.c_double)]
-    l.smafa_debug_sparse_decode.argtypes = [vp, vp, vp, u32, C.c_int, vp]
+    l.smafa_ctx_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int]
+    l.smafa_ctx_device_count.argtypes = [vp]
+    l.smafa_comm_unique_id.argtypes = [vp]
+    l.smafa_ctx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    l.smafa_ctx_comm_free.argtypes = [vp]
+    l.smafa_ctx_comm_free.restype = None
+    l.smafa_db_upload_shard.argtypes = [vp, vp, u64, u32, u64, u64, C.POINTER(vp)]
+    l.smafa_query_sharded.argtypes = [vp, vp, vp, u64, u32, i64, i64, C.POINTER(C.POINTER(Hit)), C.POINTER(u64),
+                                      C.POINTER(Stats)]
+    l.smafa_query_sharded_dev.argtypes = [vp, vp, vp, u64, u32, i64, i64, vp, u64, C.POINTER(u64), vp, C.POINTER(Stats)]
     l.smafa_db_mma_k.restype = u32
     l.smafa_db_mma_k.argtypes = [vp]
     l.smafa_encode_symbol.restype = C.c_uint8
@@ -133,16 +152,88 @@ def _words(a):
     return a
 
 
+def comm_unique_id():
+    """A fresh communicator id (rank 0 makes it, every rank of a sharded run gets a copy): bytes of COMM_ID_BYTES."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load_library().smafa_comm_unique_id(buf)
+    if rc:
+        _raise(rc)
+    return bytes(buf)
+
+
 class Context:
-    """One GPU.  kernel: 'auto' | 'popc' | 'mma'."""
+    """One GPU (device = its number), or several GPUs of this process (device = a list: every db is row-sharded
+    over them, smafa_ctx_create_multi).  kernel: 'auto' | 'popc' | 'mma'."""
 
     def __init__(self, device=0, kernel="auto"):
         self._l = load_library()
         self._h = C.c_void_p()
-        rc = self._l.smafa_ctx_create(C.byref(self._h), int(device), _KERNELS[kernel] if isinstance(kernel, str) else kernel)
+        kern = _KERNELS[kernel] if isinstance(kernel, str) else kernel
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._l.smafa_ctx_create_multi(C.byref(self._h), devs, len(device), kern)
+            self.devices = [int(d) for d in device]
+            device = self.devices[0] if self.devices else 0
+        else:
+            rc = self._l.smafa_ctx_create(C.byref(self._h), int(device), kern)
+            self.devices = [int(device)]
         if rc:
             _raise(rc)
         self.device = device
+
+    # ---- sharded runs with one process per GPU (SURVEY.md 8e; smafa_b200/dist.py drives this) ----
+    def comm_init(self, comm_id, rank, world_size):
+        """Joins the NCCL communicator `comm_id` (comm_unique_id() of rank 0).  Collective over the ranks."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        rc = self._l.smafa_ctx_comm_init(self._h, buf, int(rank), int(world_size))
+        if rc:
+            _raise(rc, self._h)
+
+    def upload_shard(self, enc, L, subject_offset, total_rows):
+        return Db(self, enc, L, subject_offset, total_rows=total_rows)
+
+    def query_sharded(self, db, q_enc, q_len, max_divergence=None, max_num_hits=None, return_stats=False):
+        """Collective: every rank passes the same queries and receives the complete answer (uint32 [n, 3])."""
+        q = _words(q_enc) if len(q_enc) else np.zeros((0, max(db.W, 1)), dtype=np.uint64)
+        hits = C.POINTER(Hit)()
+        n = C.c_uint64(0)
+        st = Stats()
+        rc = self._l.smafa_query_sharded(self._h, db.handle, q.ctypes.data, q.shape[0], int(q_len), _opt(max_divergence),
+                                         _opt(max_num_hits), C.byref(hits), C.byref(n), C.byref(st))
+        if rc:
+            _raise(rc, self._h)
+        arr = (np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint32)), shape=(n.value, 3)).copy()
+               if n.value else np.zeros((0, 3), dtype=np.uint32))
+        self._l.smafa_free(hits)
+        return (arr, st.as_dict()) if return_stats else arr
+
+    def query_sharded_ptr(self, db, q_host_ptr, Q, q_len, max_divergence=None, max_num_hits=None):
+        """smafa_query_sharded on a raw host pointer (e.g. pinned memory) -> (rows as uint32 [n, 3], stats)."""
+        hits = C.POINTER(Hit)()
+        n = C.c_uint64(0)
+        st = Stats()
+        rc = self._l.smafa_query_sharded(self._h, db.handle, q_host_ptr, int(Q), int(q_len), _opt(max_divergence),
+                                         _opt(max_num_hits), C.byref(hits), C.byref(n), C.byref(st))
+        if rc:
+            _raise(rc, self._h)
+        arr = (np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint32)), shape=(n.value, 3)).copy()
+               if n.value else np.zeros((0, 3), dtype=np.uint32))
+        self._l.smafa_free(hits)
+        return arr, st.as_dict()
+
+    def query_sharded_dev(self, db, q_dev_ptr, Q, q_len, hits_dev_ptr, hits_capacity, max_divergence=None,
+                          max_num_hits=None, stream=None):
+        """Device-resident collective variant.  -> (n_hits, stats dict)."""
+        n = C.c_uint64(0)
+        st = Stats()
+        rc = self._l.smafa_query_sharded_dev(self._h, db.handle, q_dev_ptr, int(Q), int(q_len), _opt(max_divergence),
+                                             _opt(max_num_hits), hits_dev_ptr, int(hits_capacity), C.byref(n),
+                                             stream, C.byref(st))
+        if rc == -11 and n.value > hits_capacity:
+            raise SmafaCapacityError(n.value, self._l.smafa_last_error(self._h).decode(errors="replace"))
+        if rc:
+            _raise(rc, self._h)
+        return n.value, st.as_dict()
 
     @property
     def handle(self):
@@ -226,9 +317,25 @@ class Context:
         rc = self._l.smafa_query_dev(self._h, db.handle, q_dev_ptr, int(Q), int(q_len), _opt(max_divergence),
                                      _opt(max_num_hits), hits_dev_ptr, int(hits_capacity), C.byref(n),
                                      stream, C.byref(st))
+        if rc == -11 and n.value > hits_capacity:
+            raise SmafaCapacityError(n.value, self._l.smafa_last_error(self._h).decode(errors="replace"))
         if rc:
             _raise(rc, self._h)
         return n.value, st.as_dict()
+
+    def query_ptr(self, db, q_host_ptr, Q, q_len, max_divergence=None, max_num_hits=None):
+        """smafa_query on a raw host pointer (e.g. pinned memory) -> (rows as uint32 [n, 3], stats)."""
+        hits = C.POINTER(Hit)()
+        n = C.c_uint64(0)
+        st = Stats()
+        rc = self._l.smafa_query(self._h, db.handle, q_host_ptr, int(Q), int(q_len), _opt(max_divergence),
+                                 _opt(max_num_hits), C.byref(hits), C.byref(n), C.byref(st))
+        if rc:
+            _raise(rc, self._h)
+        arr = (np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint32)), shape=(n.value, 3)).copy()
+               if n.value else np.zeros((0, 3), dtype=np.uint32))
+        self._l.smafa_free(hits)
+        return arr, st.as_dict()
 
     def merge_dev(self, cands_dev_ptr, n, max_divergence=None, max_num_hits=None, stream=None):
         out = C.c_uint64(0)
@@ -250,24 +357,6 @@ class Context:
     def last_mma_k(self):
         """int8 contraction depth per window of the last tcgen05 scan (union-row operands: K / 2); 0 before any."""
         return int(self._l.smafa_ctx_last_mma_k(self._h))
-
-    def mma_rate_ns(self, shape, n_steps=40000):
-        """ns per k-step and SM for instruction shape 0 (dense N256), 1 (2 x N128), 2 (sparse K64); see smafa_b200.h."""
-        t = C.c_double(0)
-        rc = self._l.smafa_debug_mma_rate(self._h, int(shape), int(n_steps), C.byref(t))
-        if rc:
-            _raise(rc, self._h)
-        return t.value
-
-    def debug_sparse_decode(self, a_comp, meta, n_steps=2, meta_path=0):
-        """Logical A rows the tensor core reconstructs from compressed values + metadata: int32 [n_steps, 128, 64]."""
-        a = np.ascontiguousarray(a_comp, dtype=np.int8).reshape(128, 64)
-        m = np.ascontiguousarray(meta, dtype=np.uint32).reshape(128, 4)
-        out = np.zeros((n_steps, 128, 64), dtype=np.int32)
-        rc = self._l.smafa_debug_sparse_decode(self._h, a.ctypes.data, m.ctypes.data, int(n_steps), int(meta_path), out.ctypes.data)
-        if rc:
-            _raise(rc, self._h)
-        return out
 
     def debug_mma_dump(self, db, q_enc, bound):
         """Raw tcgen05 accumulators of the first db tile: int32 [128, 256] (see smafa_b200.h)."""
@@ -297,7 +386,7 @@ class Db:
     """GPU-resident window set (the reference's WindowSet, src/lib.rs:54-60), optionally one
     row-shard of it (subject_offset = first global row)."""
 
-    def __init__(self, ctx, enc, L, subject_offset=0, keep_host=True):
+    def __init__(self, ctx, enc, L, subject_offset=0, keep_host=True, total_rows=None):
         self.ctx = ctx
         self._l = ctx._l
         e = _words(enc) if len(enc) else np.zeros((0, max((L + 11) // 12, 1)), dtype=np.uint64)
@@ -306,8 +395,12 @@ class Db:
         self.subject_offset = subject_offset
         self.host_words = e if keep_host else None
         self._h = C.c_void_p()
-        rc = self._l.smafa_db_upload(ctx.handle, e.ctypes.data if e.shape[0] else None, e.shape[0], int(L),
-                                     int(subject_offset), C.byref(self._h))
+        if total_rows is None:
+            rc = self._l.smafa_db_upload(ctx.handle, e.ctypes.data if e.shape[0] else None, e.shape[0], int(L),
+                                         int(subject_offset), C.byref(self._h))
+        else:  # one shard of a row-sharded db (one process per GPU)
+            rc = self._l.smafa_db_upload_shard(ctx.handle, e.ctypes.data if e.shape[0] else None, e.shape[0], int(L),
+                                               int(subject_offset), int(total_rows), C.byref(self._h))
         if rc:
             _raise(rc, ctx.handle)
 

@@ -21,7 +21,7 @@ NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-
                      "--expt-relaxed-constexpr"]
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-I/usr/local/cuda/include"]
 
-CU_SOURCES = ["pack.cu", "scan_popc.cu", "scan_mma.cu", "probe.cu", "guess.cu", "finalize.cu", "api.cu"]
+CU_SOURCES = ["pack.cu", "scan_popc.cu", "scan_mma.cu", "guess.cu", "finalize.cu", "merge.cu", "sharded.cu", "api.cu"]
 CXX_SOURCES = ["seqio.cpp", "commands.cpp"]
 
 

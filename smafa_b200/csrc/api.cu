@@ -2,6 +2,7 @@
 // See include/smafa_b200.h for the contract and the reference code each entry point replaces.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,17 @@ const char *smafa_global_error() { return g_err.c_str(); }
 void smafa_set_global_error(const std::string &s) { g_err = s; }
 
 static int fail(smafa_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  g_err = buf;
+  return code;
+}
+
+int smafa_fail(smafa_ctx *ctx, int code, const char *fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -52,6 +64,8 @@ extern "C" const char *smafa_status_name(int s) {
     case SMAFA_E_OOM: return "SMAFA_E_OOM";
     case SMAFA_E_INVALID: return "SMAFA_E_INVALID";
     case SMAFA_E_UNSUPPORTED: return "SMAFA_E_UNSUPPORTED";
+    case SMAFA_E_NCCL: return "SMAFA_E_NCCL";
+    case SMAFA_E_PEER: return "SMAFA_E_PEER";
     case SMAFA_E_IO: return "SMAFA_E_IO";
     case SMAFA_E_PANIC: return "SMAFA_E_PANIC";
     default: return "SMAFA_E_?";
@@ -110,10 +124,26 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   if (const char *e = getenv("SMAFA_DB_GROUP")) ctx->db_group = e[0] == '1';
   if (const char *e = getenv("SMAFA_UNION_VERIFY_NS")) { const double v = atof(e); if (v > 0) ctx->union_verify_ns = v; }
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e2 != cudaSuccess) { delete ctx; return fail(nullptr, SMAFA_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
-  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
-  cudaHostAlloc((void **)&ctx->h_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long), cudaHostAllocDefault);
-  cudaMalloc((void **)&ctx->d_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long));
+  const char *what = "cudaStreamCreate";
+  for (auto &ev : ctx->ev)
+    if (e2 == cudaSuccess) { e2 = cudaEventCreate(&ev); what = "cudaEventCreate"; }
+  if (e2 == cudaSuccess) {
+    e2 = cudaHostAlloc((void **)&ctx->h_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long), cudaHostAllocDefault);
+    what = "cudaHostAlloc(scalars)";
+  }
+  if (e2 == cudaSuccess) {
+    e2 = cudaMalloc((void **)&ctx->d_scalars, smafa_ctx::N_SCALARS * sizeof(unsigned long long));
+    what = "cudaMalloc(scalars)";
+  }
+  if (e2 == cudaSuccess) {
+    e2 = cudaMemsetAsync(ctx->d_scalars, 0, smafa_ctx::N_SCALARS * sizeof(unsigned long long), ctx->stream);
+    what = "cudaMemset(scalars)";
+  }
+  if (e2 != cudaSuccess) {
+    const int code = e2 == cudaErrorMemoryAllocation ? SMAFA_E_OOM : SMAFA_E_CUDA;
+    smafa_ctx_destroy(ctx);  // releases whatever was created (the CUDA destroy/free calls accept null handles)
+    return fail(nullptr, code, "smafa_ctx_create: %s: %s", what, cudaGetErrorString(e2));
+  }
   lap("stream, events, scalars");
   *out = ctx;
   return SMAFA_OK;
@@ -130,21 +160,26 @@ static void free_workspace(smafa_ctx *ctx) {
 
 extern "C" void smafa_ctx_destroy(smafa_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->multi) { multi_destroy(ctx); delete ctx; return; }
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  comm_free(ctx);
+  exchange_free(ctx);
   free_workspace(ctx);
   cudaFree(ctx->bound); cudaFree(ctx->hist); cudaFree(ctx->q_ref); cudaFree(ctx->q_planes);
   cudaFree(ctx->q_onehot);
   cudaFree(ctx->per_query); cudaFree(ctx->unfinished); cudaFree(ctx->q_ref2);
   cudaFree(ctx->d_scalars);
   cudaFreeHost(ctx->h_scalars);
-  for (auto &ev : ctx->ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(ctx->stream);
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 extern "C" int smafa_ctx_set_kernel(smafa_ctx *ctx, int kernel) {
   if (!ctx || kernel < 0 || kernel > 2) return fail(ctx, SMAFA_E_INVALID, "bad kernel selector %d", kernel);
+  if (ctx->multi) return multi_set(ctx, 0, kernel);
   ctx->kernel = kernel;
   return SMAFA_OK;
 }
@@ -153,11 +188,13 @@ extern "C" int smafa_ctx_set_alphabet(smafa_ctx *ctx, int alphabet) {
   if (!ctx || (alphabet != SMAFA_ALPHABET_NUCLEOTIDE && alphabet != SMAFA_ALPHABET_PROTEIN))
     return fail(ctx, SMAFA_E_INVALID, "bad alphabet selector %d", alphabet);
   ctx->alphabet = alphabet;
+  if (ctx->multi) return multi_set(ctx, 1, alphabet);
   return SMAFA_OK;
 }
 
 extern "C" int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows) {
   if (!ctx) return SMAFA_E_INVALID;
+  if (ctx->multi) return multi_set(ctx, 2, (int64_t)rows);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_workspace(ctx);
@@ -170,16 +207,21 @@ static int ensure_workspace(smafa_ctx *ctx, uint64_t rows) {
   if (ctx->ws_cap >= rows) return SMAFA_OK;
   cudaStreamSynchronize(ctx->stream);
   free_workspace(ctx);
-  CU(cudaMalloc((void **)&ctx->cand, rows * sizeof(uint64_t)));
-  CU(cudaMalloc((void **)&ctx->fw.keys_sorted, rows * sizeof(uint64_t)));
-  CU(cudaMalloc((void **)&ctx->fw.keys_sel, rows * sizeof(uint64_t)));
-  CU(cudaMalloc((void **)&ctx->fw.seg_start, MAX_BATCH_QUERIES * sizeof(uint32_t)));
-  CU(cudaMalloc((void **)&ctx->fw.seg_end, MAX_BATCH_QUERIES * sizeof(uint32_t)));
   ctx->fw.cub_temp_bytes = finalize_temp_bytes(rows);
-  CU(cudaMalloc(&ctx->fw.cub_temp, ctx->fw.cub_temp_bytes));
+  cudaError_t e = cudaMalloc((void **)&ctx->cand, rows * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->fw.keys_sorted, rows * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->fw.keys_sel, rows * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->fw.seg_start, MAX_BATCH_QUERIES * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->fw.seg_end, MAX_BATCH_QUERIES * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->fw.cub_temp, ctx->fw.cub_temp_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->hits, rows * sizeof(smafa_hit));
+  if (e != cudaSuccess) {
+    free_workspace(ctx);  // nothing half-allocated stays behind
+    return fail(ctx, e == cudaErrorMemoryAllocation ? SMAFA_E_OOM : SMAFA_E_CUDA, "candidate workspace for %llu rows: %s",
+                (unsigned long long)rows, cudaGetErrorString(e));
+  }
   ctx->fw.n_selected = ctx->d_scalars + 1;
   ctx->fw.cap = rows;
-  CU(cudaMalloc((void **)&ctx->hits, rows * sizeof(smafa_hit)));
   ctx->ws_cap = rows;
   return SMAFA_OK;
 }
@@ -210,20 +252,25 @@ static int db_reserve(smafa_ctx *ctx, smafa_db *db, uint64_t rows) {
   ncap = (ncap + 255) / 256 * 256;
   uint64_t *nref = nullptr;
   uint32_t *npl = nullptr;
-  CU(cudaMalloc((void **)&nref, std::max<uint64_t>(1, ncap * db->W) * sizeof(uint64_t)));
-  if (db->row_words) {
+  cudaError_t e = cudaMalloc((void **)&nref, std::max<uint64_t>(1, ncap * db->W) * sizeof(uint64_t));
+  if (e == cudaSuccess && db->row_words) {
     // one extra tile of rows so the POPC kernel's register prefetch never leaves the allocation
     size_t bytes = (ncap + 512) * db->row_words * sizeof(uint32_t);
-    CU(cudaMalloc((void **)&npl, bytes));
-    CU(cudaMemsetAsync(npl, 0, bytes, ctx->stream));
+    e = cudaMalloc((void **)&npl, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(npl, 0, bytes, ctx->stream);
   }
-  if (db->D) {
-    CU(cudaMemcpyAsync(nref, db->ref, db->D * db->W * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (db->row_words)
-      CU(cudaMemcpyAsync(npl, db->planes, db->D * db->row_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
-                         ctx->stream));
+  if (e == cudaSuccess && db->D) {
+    e = cudaMemcpyAsync(nref, db->ref, db->D * db->W * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess && db->row_words)
+      e = cudaMemcpyAsync(npl, db->planes, db->D * db->row_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {  // the db keeps its old arrays
+    cudaFree(nref);
+    cudaFree(npl);
+    return fail(ctx, e == cudaErrorMemoryAllocation ? SMAFA_E_OOM : SMAFA_E_CUDA, "db storage for %llu rows: %s",
+                (unsigned long long)ncap, cudaGetErrorString(e));
+  }
   cudaFree(db->ref);
   cudaFree(db->planes);
   db->ref = nref;
@@ -287,6 +334,7 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
                                smafa_db **out) {
   if (!ctx || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: null argument");
   *out = nullptr;
+  if (ctx->multi) return multi_db_upload(ctx, enc, D, L, subject_offset, out);
   if (D > 0 && (!enc || L == 0)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: D > 0 needs enc and L > 0");
   if (L > MAX_WINDOW_LEN) return fail(ctx, SMAFA_E_UNSUPPORTED, "window length %u > %u", L, MAX_WINDOW_LEN);
   CU(cudaSetDevice(ctx->device));
@@ -322,8 +370,22 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
   return SMAFA_OK;
 }
 
+// A shard of a row-sharded db: rows [subject_offset, subject_offset + D) of a db of D_total rows.
+extern "C" int smafa_db_upload_shard(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset,
+                                     uint64_t D_total, smafa_db **out) {
+  if (ctx && ctx->multi) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_upload_shard: a multi-device context shards its dbs itself");
+  if (subject_offset + D > D_total) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload_shard: rows [%llu, %llu) exceed the db's %llu rows",
+                                                (unsigned long long)subject_offset, (unsigned long long)(subject_offset + D), (unsigned long long)D_total);
+  if (D_total >= (1ull << 32)) return fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
+  int rc = smafa_db_upload(ctx, enc, D, L, subject_offset, out);
+  if (rc == SMAFA_OK) (*out)->global_rows = D_total;
+  return rc;
+}
+
 extern "C" int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n) {
   if (!ctx || !db || (n && !enc)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_append: null argument");
+  if (ctx->multi) return multi_db_append(ctx, db, enc, n);
+  if (db->global_rows) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_append: the db is one shard of a larger db");
   if (db->perm != nullptr && n) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_append: the db is stored in grouped order (SMAFA_DB_GROUP)");
   CU(cudaSetDevice(ctx->device));
   return db_add_rows(ctx, db, enc, n);
@@ -334,6 +396,7 @@ extern "C" uint32_t smafa_db_window_len(const smafa_db *db) { return db ? db->L 
 
 extern "C" void smafa_db_free(smafa_db *db) {
   if (!db) return;
+  if (db->ctx && db->ctx->multi) { multi_db_free(db); return; }
   if (db->ctx) { cudaSetDevice(db->ctx->device); cudaStreamSynchronize(db->ctx->stream); }
   cudaFree(db->ref);
   cudaFree(db->planes);
@@ -348,6 +411,7 @@ extern "C" void smafa_db_free(smafa_db *db) {
 extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len,
                                uint16_t *out) {
   if (!ctx || !db) return fail(ctx, SMAFA_E_INVALID, "smafa_distances: null argument");
+  if (ctx->multi) return multi_distances(ctx, db, q_enc, Q, q_len, out);
   if (Q == 0 || db->D == 0) return SMAFA_OK;
   if (!q_enc || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_distances: null buffer");
   if (q_len != db->L)
@@ -386,35 +450,27 @@ extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_
 
 namespace {
 
-struct QueryPlan {
-  int mode;        // ScanMode
-  uint32_t k_scan; // MODE_KTH tightening parameter
-  uint32_t k_fin;  // finalize: keep rows <= k-th smallest distance (UINT32_MAX: keep all)
-  int bound0;      // initial bound
-};
-
 constexpr int RC_OVERFLOW = 1;  // internal: candidate buffer too small for this batch
 
 }  // namespace
 
-static int validate_query(smafa_ctx *ctx, const smafa_db *db, uint64_t Q, uint32_t q_len, int64_t m, int64_t k,
-                          QueryPlan *plan) {
+int validate_query_plan(smafa_ctx *ctx, uint64_t D, uint32_t L, uint64_t Q, uint32_t q_len, int64_t m, int64_t k, QueryPlan *plan) {
   if (Q == 0) return SMAFA_OK;
   // order of the reference's checks for the first record: length (src/lib.rs:72-79), then the
   // selection's unwrap()/underflow panics (src/lib.rs:253-255,298)
-  if (db->D > 0 && q_len != db->L)
+  if (D > 0 && q_len != L)
     return fail(ctx, SMAFA_E_LENGTH_MISMATCH,
-                "Cannot compute distances between seq of length %u and windows of lengths %u", q_len, db->L);
+                "Cannot compute distances between seq of length %u and windows of lengths %u", q_len, L);
   const bool mode_b = (k >= 0 && k != 1);  // src/lib.rs:224
-  if (mode_b && k == 0 && db->D > 0) return fail(ctx, SMAFA_E_BAD_K, "attempt to subtract with overflow");
-  if (db->D == 0) return fail(ctx, SMAFA_E_EMPTY_DB, "called `Option::unwrap()` on a `None` value");
-  plan->bound0 = (int)db->L;
-  if (m >= 0 && m < (int64_t)db->L) plan->bound0 = (int)m;
+  if (mode_b && k == 0 && D > 0) return fail(ctx, SMAFA_E_BAD_K, "attempt to subtract with overflow");
+  if (D == 0) return fail(ctx, SMAFA_E_EMPTY_DB, "called `Option::unwrap()` on a `None` value");
+  plan->bound0 = (int)L;
+  if (m >= 0 && m < (int64_t)L) plan->bound0 = (int)m;
   if (!mode_b) {
     plan->mode = MODE_MIN;
     plan->k_scan = 1;
     plan->k_fin = 1;
-  } else if ((uint64_t)k >= db->D) {  // cutoff = largest distance (src/lib.rs:254): nothing to tighten
+  } else if ((uint64_t)k >= D) {  // cutoff = largest distance (src/lib.rs:254): nothing to tighten
     plan->mode = MODE_FIXED;
     plan->k_scan = 0;
     plan->k_fin = UINT32_MAX;
@@ -424,6 +480,10 @@ static int validate_query(smafa_ctx *ctx, const smafa_db *db, uint64_t Q, uint32
     plan->k_fin = (uint32_t)k;
   }
   return SMAFA_OK;
+}
+
+static int validate_query(smafa_ctx *ctx, const smafa_db *db, uint64_t Q, uint32_t q_len, int64_t m, int64_t k, QueryPlan *plan) {
+  return validate_query_plan(ctx, db->D, db->L, Q, q_len, m, k, plan);
 }
 
 static uint32_t pick_chunk(const smafa_ctx *ctx, uint64_t D, uint64_t n_qtiles, uint32_t tile) {
@@ -470,12 +530,31 @@ static int guess_bound(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref
 
 // How many db windows share one accumulator in the next tcgen05 scan (scan_mma.cu, UPR).  A union row of u windows
 // costs 1/u of the tensor work and of the accumulator drain per comparison, but every row that passes its (looser)
-// filter sends u windows to the exact re-check.  Per comparison:  cost(u) = t_u + c_v * f_u,  t_u = scan time per
-// comparison measured on B200 at L = 60 (100 k x 1 M: 9.6 ms, 6.4 ms, ~4.3 ms per 1e11), c_v = 1.5 ns per verified
-// window, f_u = fraction of the rows of degree u that pass at need = L - b0 -- measured on a
-// strided sample of this batch against this db, so related windows, skewed base composition or a loose bound
-// simply show up as a larger f_u and a smaller degree.  Small batches use the thresholds the model gives for
-// unrelated uniform windows (pass probability 7/16 or 37/64 per position: need >= 3L/4, 7L/8).
+// filter sends u windows to the exact re-check.  Per comparison:  cost(u) = t_u + c_v * f_u.
+//   t_u = time per comparison of a scan of degree u that verifies nothing: one 128-row tile costs its MMAs (68 ns per
+//         k-step per SM at M128 x N256 x K32) or the ~400 ns accumulator drain, whichever is longer, at the ~90 % the
+//         kernel sustains, and holds 128 u windows x 256 queries.  L = 60: 9.7e-5, 6.2e-5, 4.2e-5 ns (measured).
+//   f_u = fraction of the (query, row) pairs of degree u that pass at need = L - b0 -- measured on a strided sample of
+//         THIS batch against THIS db (union_sample_kernel), so related windows, skewed base composition or a loose
+//         bound simply show up as a larger f_u and a smaller degree.
+//   c_v = 0.03 ns per window sent to the re-check.  Calibrated on forced degrees over six db shapes x several bounds
+//         (profiles/r02_union_calib.log, scripts/union_calib.py): the measured cost per verified window is 0.01-0.03 ns
+//         while the verifier warps keep up and rises towards 0.1 ns once rows pass by the percent (ring-full waits);
+//         with 0.03 the model picks the fastest forced degree in all 17 (db, bound) cases of that log.  (Round 1 used
+//         1.5 ns, the cost of an EMITTED candidate -- those are the same at every degree and cancel out.)
+// The sample costs a kernel and a host read-back, so its verdict is kept with the db and reused for the next scans at
+// the same need with a similar batch size (re-sampled every 32 scans and whenever the db has grown by a quarter).
+// Batches too small to sample use the thresholds this model gives for unrelated uniform windows: a position passes a
+// union of u windows with probability p_u = 1 - (3/4)^u, a row passes when Binomial(L, p_u) >= need; the degree is
+// worth it while f_u stays below (t_{u-1} - t_u) / c_v ~ 1e-3, i.e. need >= L p_u + 3.1 sqrt(L p_u (1 - p_u)).
+static double union_scan_ns(const smafa_ctx *ctx, uint32_t L, uint32_t u) {
+  // k-steps per tile: union rows are one-hot over 4 bases (K = 256, or 128 for L <= 31); single rows use the db's own
+  // encoding -- +-1 features by default (K = 192 / 96)
+  const uint32_t ksteps = u > 1 ? (L <= 31 ? 4 : 8) : (L <= 30 ? 3 : 6);
+  const double tile_ns = std::max(68.0 * ksteps, 400.0) / 0.9;
+  return tile_ns / (128.0 * u * 256.0 * (double)ctx->num_sms);
+}
+
 static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint32_t nq, int b0, cudaStream_t s,
                                   int *launches, int *rc_out) {
   *rc_out = SMAFA_OK;
@@ -486,9 +565,14 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
   if (max_u == 1 || 2 * need < (int)db->L) return 1;  // a union of two windows differs from a query in < L/2 positions far too often
   if (ctx->mma_union_force >= 1) return std::min<uint32_t>((uint32_t)ctx->mma_union_force, max_u);
   const double pairs = (double)nq * (double)db->D;
+  const bool debug = getenv("SMAFA_UNION_DEBUG") != nullptr;
+  if (pairs >= 2e9 && db->D >= 65536 && nq >= 1024 && !debug && db->pick_degree && db->pick_need == need && db->pick_age < 32 &&
+      nq >= db->pick_nq / 2 && nq <= db->pick_nq * 2 && db->D >= db->pick_rows && db->D <= db->pick_rows + db->pick_rows / 4) {
+    db->pick_age++;
+    return std::min(db->pick_degree, max_u);
+  }
   if (db->perm != nullptr && max_u > 3) {
-    // Grouped db (experimental): rows up to 16 windows wide; always sampled (such a db has >= 65536 windows).  t_u for the
-    // wider rows: a tile costs what it costs at degree 3 (MMA-bound, ~620 ns) and holds 128 u windows.
+    // Grouped db (experimental): rows up to 16 windows wide; always sampled (such a db has >= 65536 windows).
     const uint32_t q_stride = (nq + 4095) / 4096;
     const uint32_t n_d = (uint32_t)std::min<uint64_t>(1024, db->D);
     const uint32_t d_stride = (uint32_t)(db->D / n_d);
@@ -499,21 +583,27 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
     if (e != cudaSuccess) { *rc_out = fail(ctx, SMAFA_E_CUDA, "union sample: %s", cudaGetErrorString(e)); return 1; }
     const double n_s = std::max<double>(1.0, (double)ctx->h_scalars[14]);
     static const uint32_t deg[6] = {1, 2, 3, 4, 8, 16};
-    static const double t_w[6] = {9.6e-5, 6.4e-5, 4.3e-5, 3.3e-5, 1.7e-5, 0.85e-5};
+    if (debug)
+      fprintf(stderr, "[smafa union] need %d: passing fraction of rows of degree 1/2/3/4/8/16 = %.3e / %.3e / %.3e / %.3e / %.3e / %.3e (%.0f samples)\n",
+              need, ctx->h_scalars[8] / n_s, ctx->h_scalars[9] / n_s, ctx->h_scalars[10] / n_s, ctx->h_scalars[11] / n_s,
+              ctx->h_scalars[12] / n_s, ctx->h_scalars[13] / n_s, n_s);
     uint32_t best = 1;
     double best_cost = 0;
     for (int i = 0; i < 6 && deg[i] <= max_u; ++i) {
-      const double cost = t_w[i] + ctx->union_verify_ns * (double)ctx->h_scalars[8 + i] / n_s;
+      const double cost = union_scan_ns(ctx, db->L, deg[i]) + ctx->union_verify_ns * (double)ctx->h_scalars[8 + i] / n_s;
       if (i == 0 || cost < best_cost) { best = deg[i]; best_cost = cost; }
     }
+    db->pick_need = need; db->pick_degree = best; db->pick_age = 0; db->pick_nq = nq; db->pick_rows = db->D;
     return best;
   }
   if (pairs < 2e9 || db->D < 65536 || nq < 1024) {
-    if (max_u >= 3 && 8 * need >= 7 * (int)db->L) return 3;
-    return 4 * need >= 3 * (int)db->L ? 2 : 1;
+    const double Ld = (double)db->L;
+    auto worth = [&](double p) { return (double)need >= Ld * p + 3.1 * sqrt(Ld * p * (1.0 - p)); };
+    if (max_u >= 3 && worth(37.0 / 64.0)) return 3;
+    return worth(7.0 / 16.0) ? 2 : 1;
   }
-  // 4096 x 1024 = 4.2 M sampled pairs: one count is 2.4e-7 of the rows, i.e. 3.6e-7 ns in the cost below (the t_u are
-  // 2e-5 apart); ncu: 81 us per launch at 4096 x 2048 (profiles/r01_launches_v9_summary.txt), 1.9 % of a 100 k x 1 M step
+  // 4096 x 1024 = 4.2 M sampled pairs: one count is 2.4e-7 of the rows, i.e. 7e-9 ns in the cost below (the t_u are
+  // 2e-5 apart); ncu: 81 us per launch at 4096 x 2048 (profiles/r01_launches_v9_summary.txt)
   const uint32_t q_stride = (nq + 4095) / 4096;
   const uint32_t n_d = (uint32_t)std::min<uint64_t>(1024, db->D);
   const uint32_t d_stride = (uint32_t)(db->D / n_d);
@@ -523,22 +613,25 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { *rc_out = fail(ctx, SMAFA_E_CUDA, "union sample: %s", cudaGetErrorString(e)); return 1; }
   const double n_s = std::max<double>(1.0, (double)ctx->h_scalars[11]);
-  static const double t_u[3] = {9.6e-5, 6.4e-5, 4.3e-5};  // ns per comparison
+  if (debug)
+    fprintf(stderr, "[smafa union] need %d: passing fraction of rows of degree 1/2/3 = %.3e / %.3e / %.3e (%.0f samples)\n", need,
+            ctx->h_scalars[8] / n_s, ctx->h_scalars[9] / n_s, ctx->h_scalars[10] / n_s, n_s);
   uint32_t best = 1;
   double best_cost = 0;
   for (uint32_t u = 1; u <= max_u; ++u) {
-    const double cost = t_u[u - 1] + ctx->union_verify_ns * (double)ctx->h_scalars[8 + u - 1] / n_s;
+    const double cost = union_scan_ns(ctx, db->L, u) + ctx->union_verify_ns * (double)ctx->h_scalars[8 + u - 1] / n_s;
     if (u == 1 || cost < best_cost) { best = u; best_cost = cost; }
   }
+  db->pick_need = need; db->pick_degree = best; db->pick_age = 0; db->pick_nq = nq; db->pick_rows = db->D;
   return best;
 }
 
 // One batch (<= 2^20 queries, words already on the device).  Leaves *n_rows rows in ctx->hits.
 static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
-                     const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st) {
+                     const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st, const BatchOut &out = BatchOut()) {
   int rc;
   // Candidate rows: a tight bound emits about a row per query, so the workspace starts at 32 rows per query
-  // (1 Mi..32 Mi; a 32 Mi-row workspace is 1.4 GB of cudaMalloc, most of a small run's start-up) and run_range
+  // (1 Mi..32 Mi; a 32 Mi-row workspace is 1.4 GB of cudaMalloc, most of a small run's start-up) and run_query_range
   // grows it to what a batch turned out to need.
   uint64_t want_cap = ctx->cand_cap_request;
   if (!want_cap) {
@@ -678,6 +771,7 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       st->kernel_used = kernel == -1 ? 0 : (uint32_t)kernel;
       st->kernel_launches += launches;
       st->guess_bound = g;
+      if (kernel == SMAFA_KERNEL_MMA) st->union_degree = ctx->mma_union_used;
     }
     if (kernel != -1 && (int)(ctx->h_scalars[2] & 0xffffffffu) != 0) {
       // a query holds words that are not valid one-hot codes: redo the batch on the reference
@@ -691,8 +785,17 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   ctx->cand_needed = n_cand;
   if (n_cand > ctx->ws_cap) return RC_OVERFLOW;
   if (db->perm != nullptr) launch_remap_subjects(ctx->cand, n_cand, db->perm, s);  // grouped db: rows -> subject numbers
-  int fl = launch_finalize(ctx->fw, ctx->cand, n_cand, Qb, plan.k_fin, q_base, db->subject_offset, ctx->hits,
-                           ctx->ws_cap, ctx->h_scalars + 1, s);
+  int fl = launch_finalize_select(ctx->fw, ctx->cand, n_cand, Qb, plan.k_fin, s);
+  if (out.block) {
+    // sharded query: the selected keys join this shard's send block; their number stays on the device (merge.cu)
+    fl += launch_block_append(ctx->fw.keys_sel, ctx->fw.n_selected, n_cand, q_base, db->subject_offset, out.block, out.block_cap, s);
+    CU(cudaGetLastError());
+    if (st) st->kernel_launches += fl;
+    *n_rows = UINT64_MAX;
+    return SMAFA_OK;
+  }
+  fl += launch_keys_to_hits(ctx->fw, n_cand, q_base, db->subject_offset, out.hits ? out.hits : ctx->hits,
+                            out.hits ? out.hits_cap : ctx->ws_cap, ctx->h_scalars + 1, s);
   CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
   if (st) st->kernel_launches += fl;
@@ -700,17 +803,16 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
   return SMAFA_OK;
 }
 
-// Runs [q0, q0+n) of the device-resident queries, splitting on candidate overflow.  `sink` gets
-// each finished batch (rows in ctx->hits).
-template <class Sink>
-static int run_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint64_t q0, uint64_t n, uint64_t q_base,
-                     const QueryPlan &plan, cudaStream_t s, smafa_stats *st, Sink &&sink) {
+// Runs queries [0, n) of the device-resident words at q_dev, splitting on candidate overflow.  `sink` gets each
+// finished batch (see BatchOut for where its rows are).  Reported query numbers start at q_base.
+int run_query_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint64_t n, uint64_t q_base, const QueryPlan &plan,
+                    cudaStream_t s, smafa_stats *st, const BatchOut &out, const BatchSink &sink) {
   uint64_t done = 0;
   while (done < n) {
     uint64_t nb = std::min<uint64_t>(n - done, MAX_BATCH_QUERIES);
     for (;;) {
       uint64_t rows = 0;
-      int rc = run_batch(ctx, db, q_dev + (q0 + done) * db->W, (uint32_t)nb, (uint32_t)(q_base + q0 + done), plan, &rows, s, st);
+      int rc = run_batch(ctx, db, q_dev + done * db->W, (uint32_t)nb, (uint32_t)(q_base + done), plan, &rows, s, st, out);
       if (rc == RC_OVERFLOW) {
         if (st) st->retries++;
         // the counter kept counting past the capacity, so the need is known (a lower bound of it when the batch
@@ -730,7 +832,7 @@ static int run_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, 
         continue;
       }
       if (rc) return rc;
-      rc = sink(rows);
+      rc = sink(done, nb, rows);
       if (rc) return rc;
       break;
     }
@@ -739,12 +841,15 @@ static int run_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, 
   return SMAFA_OK;
 }
 
+int ensure_query_words(smafa_ctx *ctx, size_t words) { return ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, words); }
+
 extern "C" int smafa_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len,
                            int64_t m, int64_t k, smafa_hit **hits, uint64_t *n_hits, smafa_stats *stats) {
   if (!ctx || !db || !hits || !n_hits) return fail(ctx, SMAFA_E_INVALID, "smafa_query: null argument");
   *hits = nullptr;
   *n_hits = 0;
   if (stats) memset(stats, 0, sizeof *stats);
+  if (ctx->multi) return multi_query(ctx, db, q_enc, Q, q_len, m, k, hits, n_hits, stats);
   QueryPlan plan{};
   int rc = validate_query(ctx, db, Q, q_len, m, k, &plan);
   if (rc || Q == 0) return rc;
@@ -752,35 +857,41 @@ extern "C" int smafa_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   cudaEventRecord(ctx->ev[2], s);
-  std::vector<smafa_hit> all;
+  // the answer grows in the buffer the caller will own: rows go device -> that buffer, nothing in between
+  smafa_hit *all = nullptr;
+  uint64_t n_all = 0, cap_all = 0;
   const uint64_t slab = MAX_BATCH_QUERIES;
-  for (uint64_t q0 = 0; q0 < Q; q0 += slab) {
+  for (uint64_t q0 = 0; q0 < Q && rc == SMAFA_OK; q0 += slab) {
     uint64_t nq = std::min(slab, Q - q0);
-    if ((rc = ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, nq * db->W))) return rc;
-    CU(cudaMemcpyAsync(ctx->q_ref, q_enc + q0 * db->W, nq * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    rc = run_range(ctx, db, ctx->q_ref, 0, nq, q0, plan, s, stats, [&](uint64_t rows) -> int {
-      size_t old = all.size();
-      all.resize(old + rows);
-      if (rows) {
-        cudaError_t e = cudaMemcpyAsync(all.data() + old, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2H of hits: %s", cudaGetErrorString(e));
+    if ((rc = ensure_buf(ctx, ctx->q_ref, ctx->q_ref_cap, nq * db->W))) break;
+    cudaError_t e = cudaMemcpyAsync(ctx->q_ref, q_enc + q0 * db->W, nq * db->W * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { rc = fail(ctx, SMAFA_E_CUDA, "H2D of queries: %s", cudaGetErrorString(e)); break; }
+    rc = run_query_range(ctx, db, ctx->q_ref, nq, q0, plan, s, stats, BatchOut(), [&](uint64_t, uint64_t, uint64_t rows) -> int {
+      if (n_all + rows > cap_all) {
+        cap_all = std::max<uint64_t>({n_all + rows, cap_all * 2, 1024});
+        smafa_hit *grown = (smafa_hit *)realloc(all, cap_all * sizeof(smafa_hit));
+        if (!grown) return fail(ctx, SMAFA_E_OOM, "realloc of %llu hits failed", (unsigned long long)cap_all);
+        all = grown;
       }
+      if (rows) {
+        cudaError_t e2 = cudaMemcpyAsync(all + n_all, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToHost, s);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
+        if (e2 != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2H of hits: %s", cudaGetErrorString(e2));
+      }
+      n_all += rows;
       return SMAFA_OK;
     });
-    if (rc) return rc;
   }
+  if (rc) { free(all); return rc; }
   cudaEventRecord(ctx->ev[3], s);
   cudaEventSynchronize(ctx->ev[3]);
   if (stats) {
     cudaEventElapsedTime(&stats->total_ms, ctx->ev[2], ctx->ev[3]);
     stats->pairs = Q * db->D;
   }
-  smafa_hit *out = (smafa_hit *)malloc(std::max<size_t>(1, all.size()) * sizeof(smafa_hit));
-  if (!out) return fail(ctx, SMAFA_E_OOM, "malloc of %zu hits failed", all.size());
-  memcpy(out, all.data(), all.size() * sizeof(smafa_hit));
-  *hits = out;
-  *n_hits = all.size();
+  if (!all && !(all = (smafa_hit *)malloc(sizeof(smafa_hit)))) return fail(ctx, SMAFA_E_OOM, "malloc failed");
+  *hits = all;
+  *n_hits = n_all;
   return SMAFA_OK;
 }
 
@@ -790,6 +901,7 @@ extern "C" int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_
   if (!ctx || !db || !n_hits) return fail(ctx, SMAFA_E_INVALID, "smafa_query_dev: null argument");
   *n_hits = 0;
   if (stats) memset(stats, 0, sizeof *stats);
+  if (ctx->multi) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_query_dev: device pointers belong to one device; use smafa_query on a multi-device context");
   QueryPlan plan{};
   int rc = validate_query(ctx, db, Q, q_len, m, k, &plan);
   if (rc || Q == 0) return rc;
@@ -798,16 +910,24 @@ extern "C" int smafa_query_dev(smafa_ctx *ctx, const smafa_db *db, const uint64_
   cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, like any CUDA API
   cudaEventRecord(ctx->ev[2], s);
   uint64_t total = 0;
-  rc = run_range(ctx, db, q_enc_dev, 0, Q, 0, plan, s, stats, [&](uint64_t rows) -> int {
-    if (rows && hits_dev && total + rows <= hits_capacity) {
-      // stream-ordered: the next batch's finalize (the next writer of ctx->hits) queues behind this copy, and the
-      // event wait at the end of the call covers the last one
-      cudaError_t e = cudaMemcpyAsync(hits_dev + total, ctx->hits, rows * sizeof(smafa_hit), cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return fail(ctx, SMAFA_E_CUDA, "D2D of hits: %s", cudaGetErrorString(e));
-    }
-    total += rows;
-    return SMAFA_OK;
-  });
+  // Every batch writes its rows behind the previous one's, straight into the caller's buffer; a batch that does not
+  // fit writes nothing (keys_to_hits_kernel) and only reports its row count.
+  for (uint64_t done = 0; done < Q && rc == SMAFA_OK;) {
+    const uint64_t nq = std::min<uint64_t>(Q - done, MAX_BATCH_QUERIES);
+    BatchOut out;
+    const uint64_t room = total < hits_capacity && hits_dev ? hits_capacity - total : 0;
+    out.hits = room ? hits_dev + total : ctx->hits;
+    out.hits_cap = room;  // 0: count only
+    rc = run_query_range(ctx, db, q_enc_dev + done * db->W, nq, done, plan, s, stats, out, [&](uint64_t, uint64_t, uint64_t rows) -> int {
+      // run_query_range may split a slab into several batches: the next one must land behind this one
+      total += rows;
+      const uint64_t left = total < hits_capacity && hits_dev ? hits_capacity - total : 0;
+      out.hits = left ? hits_dev + total : ctx->hits;
+      out.hits_cap = left;
+      return SMAFA_OK;
+    });
+    done += nq;
+  }
   if (rc) return rc;
   cudaEventRecord(ctx->ev[3], s);
   cudaEventSynchronize(ctx->ev[3]);
@@ -826,6 +946,7 @@ extern "C" int smafa_merge_dev(smafa_ctx *ctx, smafa_hit *cands_dev, uint64_t n,
                                void *stream) {
   if (!ctx || !n_out) return fail(ctx, SMAFA_E_INVALID, "smafa_merge_dev: null argument");
   *n_out = 0;
+  if (ctx->multi) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_merge_dev: device pointers belong to one device");
   if (n == 0) return SMAFA_OK;
   if (!cands_dev) return fail(ctx, SMAFA_E_INVALID, "smafa_merge_dev: null buffer");
   (void)m;  // every shard already applied --max-divergence
@@ -887,6 +1008,8 @@ extern "C" uint64_t smafa_apply_limit_per_sequence(smafa_hit *hits, uint64_t n, 
 // old centroids always have lower indices than in-batch ones), else founds a new centroid.
 extern "C" int smafa_cluster(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t,
                              uint32_t *centroid_of, uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats) {
+  // the greedy is strictly sequential (src/cluster.rs:45-74): a multi-device context runs it on its first device
+  if (ctx && ctx->multi) ctx = multi_first(ctx);
   return cluster_impl(ctx, enc, n, L, t, centroid_of, n_centroids, n_comparisons, stats, UINT64_MAX);
 }
 
@@ -950,7 +1073,7 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
     old_hits.clear();
     in_hits.clear();
     auto collect = [&](std::vector<smafa_hit> &dst) {
-      return [&dst, ctx, s](uint64_t rows) -> int {
+      return [&dst, ctx, s](uint64_t, uint64_t, uint64_t rows) -> int {
         size_t old = dst.size();
         dst.resize(old + rows);
         if (rows) {
@@ -962,12 +1085,12 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
       };
     };
     if (C > 0) {
-      rc = run_range(ctx, cdb, ctx->q_ref, 0, B, 0, plan_old, s, stats, collect(old_hits));
+      rc = run_query_range(ctx, cdb, ctx->q_ref, B, 0, plan_old, s, stats, BatchOut(), collect(old_hits));
       if (rc) break;
       pairs += B * C;
     }
     lap(1);
-    rc = run_range(ctx, bdb, ctx->q_ref, 0, B, 0, plan_in, s, stats, collect(in_hits));
+    rc = run_query_range(ctx, bdb, ctx->q_ref, B, 0, plan_in, s, stats, BatchOut(), collect(in_hits));
     if (rc) break;
     pairs += B * B;
     lap(2);
@@ -1037,6 +1160,7 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
 extern "C" int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t bound,
                                     int32_t *out) {
   if (!ctx || !db || !q_enc || !out || Q == 0 || Q > 256) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_dump: bad argument");
+  if (ctx->multi) return fail(ctx, SMAFA_E_UNSUPPORTED, "debug hooks need a single-device context");
   if (!mma_supported(db) || db->D == 0) return fail(ctx, SMAFA_E_UNSUPPORTED, "db not eligible for the MMA kernel");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -1068,26 +1192,13 @@ extern "C" int smafa_debug_mma_dump(smafa_ctx *ctx, const smafa_db *db, const ui
 // every SM issues `mmas_per_cta` back-to-back M128xN256xK32 kind::i8 MMAs on resident operands.
 extern "C" int smafa_debug_mma_peak(smafa_ctx *ctx, uint32_t mmas_per_cta, double *tops) {
   if (!ctx || !tops || mmas_per_cta == 0) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_peak: bad argument");
+  if (ctx->multi) ctx = multi_first(ctx);
   CU(cudaSetDevice(ctx->device));
   float ms = 0;
   int rc = mma_peak_probe(ctx, mmas_per_cta, &ms);
   if (rc) return rc;
   *tops = 2.0 * 128 * 256 * 32 * (double)mmas_per_cta * ctx->num_sms / (ms * 1e-3) / 1e12;
   return SMAFA_OK;
-}
-
-extern "C" int smafa_debug_mma_rate(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step) {
-  if (!ctx || !ns_per_step || n_steps == 0 || shape < 0 || shape > 2) return fail(ctx, SMAFA_E_INVALID, "smafa_debug_mma_rate: bad argument");
-  CU(cudaSetDevice(ctx->device));
-  return mma_rate_probe(ctx, shape, n_steps, ns_per_step);
-}
-
-extern "C" int smafa_debug_sparse_decode(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path,
-                                         int32_t *out) {
-  if (!ctx || !a_comp || !meta || !out || n_steps < 1 || n_steps > 2 || meta_path < 0 || meta_path > 1)
-    return fail(ctx, SMAFA_E_INVALID, "smafa_debug_sparse_decode: bad argument");
-  CU(cudaSetDevice(ctx->device));
-  return sparse_decode_probe(ctx, a_comp, meta, n_steps, meta_path, out);
 }
 
 extern "C" uint32_t smafa_ctx_last_mma_k(const smafa_ctx *ctx) { return ctx ? ctx->last_mma_k : 0; }

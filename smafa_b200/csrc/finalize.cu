@@ -91,33 +91,39 @@ size_t finalize_temp_bytes(uint64_t cap) {
   return (a > b ? a : b) + 256;
 }
 
-int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k,
-                    uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out, uint64_t hits_cap,
-                    unsigned long long *n_out_pinned, cudaStream_t s) {
-  int launches = 0;
+int launch_finalize_select(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k, cudaStream_t s) {
   if (n == 0) {
     cudaMemsetAsync(ws.n_selected, 0, sizeof(unsigned long long), s);
-    keys_to_hits_kernel<<<1, 32, 0, s>>>(ws.keys_sel, ws.n_selected, hits_cap, q_base, subject_offset, hits_out,
-                                         n_out_pinned);
-    return 1;
+    return 0;
   }
   int q_bits = 1;
   while ((1ull << q_bits) < n_queries && q_bits < 20) ++q_bits;
   size_t tb = ws.cub_temp_bytes;
   cub::DeviceRadixSort::SortKeys(ws.cub_temp, tb, keys, ws.keys_sorted, (int64_t)n, 0, KEY_Q_SHIFT + q_bits, s);
-  launches += 4;  // histogram + onesweep passes (CUB-internal, approximate)
+  // CUB's onesweep sort: one histogram kernel, one exclusive-sum kernel, one pass per 8-bit digit
+  int launches = 2 + (KEY_Q_SHIFT + q_bits + 7) / 8;
   segment_bounds_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.keys_sorted, n, ws.seg_start, ws.seg_end);
   launches += 1;
   KeepWithinKth pred{ws.keys_sorted, ws.seg_start, ws.seg_end, k};
   tb = ws.cub_temp_bytes;
   cub::DeviceSelect::If(ws.cub_temp, tb, ws.keys_sorted, ws.keys_sel, ws.n_selected, (int64_t)n, pred, s);
-  launches += 2;
-  unsigned blocks = (unsigned)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  launches += 2;  // CUB select: init + sweep
+  return launches;
+}
+
+int launch_keys_to_hits(FinalizeWorkspace &ws, uint64_t n_max, uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out,
+                        uint64_t hits_cap, unsigned long long *n_out_pinned, cudaStream_t s) {
+  unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_max + 255) / 256, 148 * 8));
   keys_to_hits_kernel<<<blocks, 256, 0, s>>>(ws.keys_sel, ws.n_selected, hits_cap, q_base, subject_offset, hits_out,
                                              n_out_pinned);
-  launches += 1;
-  return launches;
+  return 1;
+}
+
+int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k,
+                    uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out, uint64_t hits_cap,
+                    unsigned long long *n_out_pinned, cudaStream_t s) {
+  int launches = launch_finalize_select(ws, keys, n, n_queries, k, s);
+  return launches + launch_keys_to_hits(ws, n, q_base, subject_offset, hits_out, hits_cap, n_out_pinned, s);
 }
 
 }  // namespace smafa

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -11,6 +12,24 @@ constexpr uint64_t DEFAULT_CAND_CAP = 32ull << 20;     // largest candidate work
 // Default of smafa_ctx::mma_union: the largest union degree (windows per accumulator) dbs are packed for.
 constexpr uint32_t SMAFA_MMA_UNION_DEFAULT = 3;
 constexpr uint64_t MAX_AUTO_CAND_CAP = 256ull << 20;  // largest the workspace grows to on its own before a batch is split
+
+// The candidate exchange of a sharded query (sharded.cu): this shard's send block, the receive area of all blocks and
+// the merge workspace (merge.cu), kept between calls; `cap` rows per block adapts to the workload.
+struct SmafaExchange {
+  uint64_t *block = nullptr;      // [2 + cap]: {rows, status, keys...}
+  uint64_t *gathered = nullptr;   // [n_ranks][2 + cap]
+  uint64_t cap = 0;
+  uint32_t n_ranks = 0;
+  uint64_t cap_hint = 0;          // capacity the next exchange starts with (twice the fullest block's last need)
+  smafa::MergeWorkspace mw;
+  smafa_hit *hits = nullptr;      // [n_ranks * cap] merged rows when the caller gave no device buffer
+  unsigned long long *info_dev = nullptr;  // [0..3] merge results (merge.cu), [4] rows selected
+  unsigned long long *info_host = nullptr; // pinned mirror
+  cudaEvent_t ev[2] = {nullptr, nullptr};  // local part done / merge done (smafa_stats.exchange_ms)
+};
+
+struct SmafaComm;   // NCCL communicator of a one-process-per-GPU run (sharded.cu)
+struct SmafaMulti;  // the per-device contexts behind a multi-device context (sharded.cu)
 
 struct smafa_ctx {
   int device = 0;
@@ -22,10 +41,11 @@ struct smafa_ctx {
   bool auto_prefers_mma = true;
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   uint32_t mma_union = 1;         // largest union degree dbs get operand images for (1..3 windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
-  double union_verify_ns = 1.5;   // cost of one verified window in pick_union_degree's model; SMAFA_UNION_VERIFY_NS (calibration)
+  double union_verify_ns = 0.03;  // cost of one verified window in pick_union_degree's model (profiles/r02_union_calib.log); SMAFA_UNION_VERIFY_NS
   bool db_group = false;          // SMAFA_DB_GROUP=1 (experimental, off): large nucleotide dbs are stored in similarity-grouped order (api.cu group_order)
   int mma_union_force = 0;        // SMAFA_MMA_UNION_FORCE=u: every tcgen05 scan that starts at need >= L/2 uses degree u whatever the sample says (tests)
   uint32_t mma_union_pick = 1;    // degree of the next mma_scan (set per scan by run_batch)
+  uint32_t mma_union_used = 0;    // degree the last mma_scan really ran with (1 when the db lacks the picked image)
   uint32_t last_mma_k = 0;        // int8 contraction depth per WINDOW of the last tcgen05 scan (K / windows per row)
   int alphabet = 0;               // Alphabet of the dbs uploaded next and of smafa_cluster input (smafa_ctx_set_alphabet)
   bool disable_prepass = false;   // SMAFA_NO_PREPASS=1 (ablation)
@@ -59,6 +79,10 @@ struct smafa_ctx {
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;  // pinned mirror
   int *d_scratch_flag() { return reinterpret_cast<int *>(d_scalars + 2); }
+  // sharded queries (sharded.cu)
+  SmafaExchange xchg;
+  SmafaComm *comm = nullptr;    // one process per GPU: smafa_ctx_comm_init
+  SmafaMulti *multi = nullptr;  // one process, several GPUs: smafa_ctx_create_multi (this context then owns no device state of its own)
 };
 
 struct smafa_db {
@@ -66,6 +90,8 @@ struct smafa_db {
   uint64_t D = 0, cap = 0;
   uint32_t L = 0, W = 0, row_words = 0;
   uint64_t subject_offset = 0;
+  uint64_t global_rows = 0;   // rows of the whole db this shard belongs to (0: not a shard; smafa_db_upload_shard)
+  std::vector<smafa_db *> shards;  // db of a multi-device context: one shard per device, nothing else
   int alphabet = 0;           // smafa::Alphabet of `ref` (and of every query batch run against this db)
   bool generic_only = false;  // invalid codes or L > 64: reference-layout kernel only
   uint64_t *ref = nullptr;    // [cap][W]
@@ -81,11 +107,54 @@ struct smafa_db {
   // 3 only for grouped dbs (perm != nullptr)
   uint8_t *union_img[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t union_cap[5] = {0, 0, 0, 0, 0};     // in tiles
+  // last sampled choice of pick_union_degree (api.cu), reused for the next scans of similar batches at the same need
+  mutable int pick_need = -1;
+  mutable uint32_t pick_degree = 0, pick_age = 0, pick_nq = 0;
+  mutable uint64_t pick_rows = 0;
 };
 
 // Degrees (windows per accumulator) a union-row image can have, and the slot of a degree in smafa_db::union_img (-1: none)
 constexpr uint32_t UNION_DEGREES[5] = {2, 3, 4, 8, 16};
 inline int union_slot(uint32_t u) { return u == 2 ? 0 : u == 3 ? 1 : u == 4 ? 2 : u == 8 ? 3 : u == 16 ? 4 : -1; }
+
+// ---- api.cu internals shared with sharded.cu ----
+struct QueryPlan {
+  int mode;        // smafa::ScanMode
+  uint32_t k_scan; // MODE_KTH tightening parameter
+  uint32_t k_fin;  // finalize: keep rows <= k-th smallest distance (UINT32_MAX: keep all)
+  int bound0;      // initial bound
+};
+// Where a batch's answer goes.  Default: smafa_hit rows in ctx->hits, count on the host.  hits != nullptr: rows are
+// written there instead (capacity hits_cap).  block != nullptr: no rows at all -- the selected keys are appended to a
+// send block (merge.cu) without any host read-back; the row count then stays on the device.
+struct BatchOut {
+  smafa_hit *hits = nullptr;
+  uint64_t hits_cap = 0;
+  uint64_t *block = nullptr;
+  uint64_t block_cap = 0;
+};
+// Checks the arguments of a query in the reference's order and fills the plan; D_total = rows of the whole db.
+int validate_query_plan(smafa_ctx *ctx, uint64_t D_total, uint32_t db_len, uint64_t Q, uint32_t q_len, int64_t m, int64_t k, QueryPlan *plan);
+// Runs queries [0, n) (device words, on db's device) against db, splitting on candidate overflow.  Per finished batch:
+// sink(first query of the batch, queries in it, rows) -- rows = UINT64_MAX in block mode (count on the device).
+typedef std::function<int(uint64_t, uint64_t, uint64_t)> BatchSink;
+int run_query_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint64_t n, uint64_t q_base, const QueryPlan &plan,
+                    cudaStream_t s, smafa_stats *st, const BatchOut &out, const BatchSink &sink);
+int smafa_fail(smafa_ctx *ctx, int code, const char *fmt, ...);
+int ensure_query_words(smafa_ctx *ctx, size_t words);  // ctx->q_ref
+
+// ---- sharded.cu: entry points api.cu forwards to for a multi-device context ----
+void multi_destroy(smafa_ctx *ctx);
+int multi_set(smafa_ctx *ctx, int what, int64_t value);  // 0 kernel, 1 alphabet, 2 candidate capacity
+int multi_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset, smafa_db **out);
+int multi_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n);
+void multi_db_free(smafa_db *db);
+int multi_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len, uint16_t *out);
+int multi_query(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, uint64_t Q, uint32_t q_len, int64_t m, int64_t k,
+                smafa_hit **hits, uint64_t *n_hits, smafa_stats *stats);
+smafa_ctx *multi_first(smafa_ctx *ctx);  // the context of the first device (cluster and the debug hooks run there)
+void exchange_free(smafa_ctx *ctx);
+void comm_free(smafa_ctx *ctx);
 
 const char *smafa_global_error();
 void smafa_set_global_error(const std::string &s);
@@ -99,6 +168,3 @@ void mma_db_free(smafa_db *db);
 // returns kernels launched (>= 0) or a negative smafa_status
 int mma_scan(smafa_ctx *ctx, const smafa_db *db, smafa::ScanParams &p, cudaStream_t s, int32_t *dump = nullptr);
 int mma_peak_probe(smafa_ctx *ctx, uint32_t mmas_per_cta, float *ms);
-// probe.cu
-int mma_rate_probe(smafa_ctx *ctx, int shape, uint32_t n_steps, double *ns_per_step);
-int sparse_decode_probe(smafa_ctx *ctx, const uint8_t *a_comp, const uint32_t *meta, uint32_t n_steps, int meta_path, int32_t *out);

@@ -57,6 +57,33 @@ size_t finalize_temp_bytes(uint64_t cap);
 int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k,
                     uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out, uint64_t hits_cap,
                     unsigned long long *n_out_pinned, cudaStream_t s);
+// The two halves of launch_finalize: sort + cutoff -> ws.keys_sel / *ws.n_selected (device); keys -> smafa_hit rows.
+int launch_finalize_select(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k, cudaStream_t s);
+int launch_keys_to_hits(FinalizeWorkspace &ws, uint64_t n_max, uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out,
+                        uint64_t hits_cap, unsigned long long *n_out_pinned, cudaStream_t s);
+
+// merge.cu -- multi-GPU merge of per-shard blocks (see the file header)
+struct MergeWorkspace {
+  uint32_t *seg = nullptr;       // [n_ranks][Q + 1]
+  uint64_t *merged = nullptr;    // [n_ranks * cap]
+  uint8_t *flags = nullptr;      // [n_ranks * cap]
+  uint64_t *selected = nullptr;  // [n_ranks * cap]
+  unsigned long long *n_selected = nullptr;  // device scalar
+  void *cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+  uint64_t rows = 0;             // n_ranks * cap the buffers are sized for
+  uint64_t seg_len = 0;          // n_ranks * (Q + 1) seg is sized for
+};
+size_t merge_temp_bytes(uint64_t rows);
+// block = {rows, status, keys...}: rows := 0, status as given
+void launch_block_reset(uint64_t *block, uint64_t status, cudaStream_t s);
+// appends the *n_ptr (<= n_max) selected keys of a finished batch to a send block; returns kernels launched
+int launch_block_append(const uint64_t *keys, const unsigned long long *n_ptr, uint64_t n_max, uint32_t q_off,
+                        uint64_t subject_offset, uint64_t *block, uint64_t cap, cudaStream_t s);
+// gathered = n_ranks blocks of 2 + cap u64; info_dev[0..3] = {largest announced row count, first status, its rank, rows kept}
+int launch_merge_blocks(MergeWorkspace &ws, const uint64_t *gathered, uint32_t n_ranks, uint64_t cap, uint32_t Q, uint32_t k,
+                        uint32_t q_base, smafa_hit *hits_out, uint64_t hits_cap, unsigned long long *info_dev, cudaStream_t s);
+
 // the same for degrees 1, 2, 3, 4, 8, 16 (grouped dbs): counts[0..5] passing pairs, counts[6] samples
 int launch_union_sample_wide(const uint64_t *q_ref, uint32_t Q, uint32_t q_stride, const uint64_t *d_ref, uint32_t D,
                              uint32_t d_stride, uint32_t n_d, uint32_t W, int need, unsigned long long *counts, cudaStream_t s);

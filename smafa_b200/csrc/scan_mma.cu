@@ -912,6 +912,7 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint32_t enc = use_union ? 4u : db->mma_nsym;
   const uint32_t KB = use_union ? union_kb(db) : mma_kb(db);
   ctx->last_mma_k = KB / upr;
+  ctx->mma_union_used = upr;
   const uint32_t n_qtiles = (p.Q + MMA_N - 1) / MMA_N;
   const size_t b_bytes = (size_t)n_qtiles * MMA_N * KB + (size_t)n_qtiles * MMA_N * sizeof(int16_t);  // operand tiles + q_meta
   if (ctx->q_onehot_cap < b_bytes) {
@@ -955,8 +956,10 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   cudaError_t e;
   const bool wide = mma_pb(enc, db->L) == 64;
   if (use_union) {
-    // SMAFA_MMA_UNION_STAGES4=1 (ablation): one query operand buffer and four db tile stages instead of two and two
-    static const bool stages4 = getenv("SMAFA_MMA_UNION_STAGES4") ? atoi(getenv("SMAFA_MMA_UNION_STAGES4")) != 0 : false;
+    // One query operand buffer and four db tile stages (default since round 2: 4.39 -> 4.15 ms per 1e11 comparisons at
+    // degree 3, 6.5 -> 6.16 at degree 2, whole parity suite green under it: profiles/r02_union_calib_stages4.log,
+    // r02_pytest_gpu_stages4.log); SMAFA_MMA_UNION_STAGES4=0 keeps the two-and-two shape reachable
+    static const bool stages4 = getenv("SMAFA_MMA_UNION_STAGES4") ? atoi(getenv("SMAFA_MMA_UNION_STAGES4")) != 0 : true;
     if (stages4 && wide && upr <= 3) {
       e = upr == 2 ? launch_mma<8, 4, 4, 8, true, 1, false, 2>(P, grid, s) : launch_mma<8, 4, 4, 8, true, 1, false, 3>(P, grid, s);
       if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);

@@ -4,6 +4,7 @@
 // C ABI (smafa_query / smafa_cluster) to the B200 kernels.  There is no CPU fallback for it.
 #include <unistd.h>
 
+#include <cerrno>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -90,11 +91,16 @@ struct EncodedInput {
 
 // Encodes records in order until one cannot be handled.  `expect_len` (0 = take the first
 // record's) is the window length every record must have; `mismatch` builds the panic text.
+// `expect_text` is the reference's .expect(..) message for a record needletail cannot parse.
 template <class MismatchMsg>
-EncodedInput encode_all(FastxFile file, uint32_t expect_len, int alphabet, MismatchMsg mismatch) {
+EncodedInput encode_all(FastxFile file, uint32_t expect_len, int alphabet, MismatchMsg mismatch, const char *expect_text) {
   EncodedInput in;
   in.records = std::move(file.recs);
   in.file = std::move(file);
+  if (!in.file.parse_error.empty()) {  // reached only if every record before it was fine (overwritten below otherwise)
+    in.failed = true;
+    in.failure = std::string(expect_text) + ": " + in.file.parse_error;
+  }
   if (in.records.empty()) return in;
   in.L = expect_len ? expect_len : (uint32_t)in.records[0].seq.size();
   in.W = words_for_len(in.L);
@@ -175,7 +181,7 @@ extern "C" int smafa_makedb_file_alphabet(const char *subject_fasta, const char 
     }
     EncodedInput in = encode_all(std::move(fx), 0, alphabet, [](size_t got, uint32_t want) {
       return "WindowSet seq length is " + std::to_string(want) + ", got a new sequence of length " + std::to_string(got);
-    });
+    }, "valid record");
     tm.lap("makedb: encode");
     if (in.failed) throw Panic(in.failure);
     WindowDb db;
@@ -215,8 +221,13 @@ extern "C" int smafa_db_file_load(const char *db_path, uint64_t **words, uint64_
 // src/lib.rs:208-217: File::open(..)? then the version gate
 extern "C" int smafa_db_file_check(const char *db_path) {
   return guarded([&]() -> int {
-    Bytes bytes = read_file(db_path);
-    if (bytes.size() > 16) bytes.resize(16);
+    // only the first bytes matter here; the whole file is read (once) by the command itself
+    FILE *f = fopen(db_path, "rb");
+    if (!f) throw IoError("Os { code: " + std::to_string(errno) + ", kind: NotFound, message: \"" + strerror(errno) + "\" }");
+    uint8_t head[16];
+    const size_t got = fread(head, 1, sizeof head, f);
+    fclose(f);
+    const std::vector<uint8_t> bytes(head, head + got);
     if (bytes.size() < 4) throw Panic("range end index 4 out of range for slice of length " + std::to_string(bytes.size()));
     uint64_t v = 0;
     for (int i = 0; i < 4; ++i) {
@@ -300,9 +311,10 @@ struct LazyCtx {
   int rc = SMAFA_OK;
   std::string err;
   std::thread th;
-  void start(int device, int kernel, int alphabet) {
-    th = std::thread([this, device, kernel, alphabet] {
-      rc = smafa_ctx_create(&ctx, device, kernel);
+  void start(const int *devices, int n_devices, int kernel, int alphabet) {
+    const std::vector<int> devs(devices, devices + n_devices);
+    th = std::thread([this, devs, kernel, alphabet] {
+      rc = smafa_ctx_create_multi(&ctx, devs.data(), (int)devs.size(), kernel);
       if (rc) err = smafa_last_error(nullptr);  // the error text is thread-local: carry it over
       else smafa_ctx_set_alphabet(ctx, alphabet);
     });
@@ -330,8 +342,17 @@ extern "C" int smafa_query_file(smafa_ctx *ctx, const char *db_path, const char 
 extern "C" int smafa_query_file_on_device(int device, int kernel, int alphabet, const char *db_path, const char *query_fasta,
                                           int64_t max_divergence, int64_t max_num_hits, int64_t limit_per_sequence,
                                           int out_fd, smafa_ctx **ctx_out) {
+  return smafa_query_file_on_devices(&device, 1, kernel, alphabet, db_path, query_fasta, max_divergence, max_num_hits,
+                                     limit_per_sequence, out_fd, ctx_out);
+}
+
+extern "C" int smafa_query_file_on_devices(const int *devices, int n_devices, int kernel, int alphabet, const char *db_path,
+                                           const char *query_fasta, int64_t max_divergence, int64_t max_num_hits,
+                                           int64_t limit_per_sequence, int out_fd, smafa_ctx **ctx_out) {
+  if (ctx_out) *ctx_out = nullptr;
+  if (!devices || n_devices < 1) { smafa_set_global_error("smafa_query_file_on_devices: no device given"); return SMAFA_E_INVALID; }
   LazyCtx lazy;
-  lazy.start(device, kernel, alphabet);
+  lazy.start(devices, n_devices, kernel, alphabet);
   int rc = query_file_impl(lazy, alphabet, db_path, query_fasta, max_divergence, max_num_hits, limit_per_sequence, out_fd);
   smafa_ctx *ctx = lazy.get();  // also when the inputs needed no device work: a missing GPU is reported, not ignored
   if (ctx_out) *ctx_out = ctx; else if (ctx) smafa_ctx_destroy(ctx);
@@ -340,8 +361,16 @@ extern "C" int smafa_query_file_on_device(int device, int kernel, int alphabet, 
 
 extern "C" int smafa_cluster_file_on_device(int device, int kernel, int alphabet, const char *input_fasta,
                                             uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out) {
+  return smafa_cluster_file_on_devices(&device, 1, kernel, alphabet, input_fasta, max_divergence, out_fd, ctx_out);
+}
+
+extern "C" int smafa_cluster_file_on_devices(const int *devices, int n_devices, int kernel, int alphabet, const char *input_fasta,
+                                             uint32_t max_divergence, int out_fd, smafa_ctx **ctx_out) {
+  if (ctx_out) *ctx_out = nullptr;
+  if (!devices || n_devices < 1) { smafa_set_global_error("smafa_cluster_file_on_devices: no device given"); return SMAFA_E_INVALID; }
   LazyCtx lazy;
-  lazy.start(device, kernel, alphabet);
+  // the greedy is sequential (src/cluster.rs:45-74): one device does all of it, the others would only idle
+  lazy.start(devices, 1, kernel, alphabet);
   int rc = cluster_file_impl(lazy, alphabet, input_fasta, max_divergence, out_fd);
   smafa_ctx *ctx = lazy.get();
   if (ctx_out) *ctx_out = ctx; else if (ctx) smafa_ctx_destroy(ctx);
@@ -363,7 +392,7 @@ static int query_file_impl(LazyCtx &lazy, int alphabet, const char *db_path, con
     EncodedInput in = encode_all(std::move(fx), db.L, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
-    });
+    }, "Failed to parse query sequence");
     tm.lap("query: encode");
     const bool mode_b = max_num_hits >= 0 && max_num_hits != 1;  // src/lib.rs:224
     FdWriter out(out_fd);
@@ -448,7 +477,7 @@ static int cluster_file_impl(LazyCtx &lazy, int alphabet, const char *input_fast
     EncodedInput in = encode_all(std::move(fx), 0, alphabet, [](size_t got, uint32_t want) {
       return "Cannot compute distances between seq of length " + std::to_string(got) + " and windows of lengths " +
              std::to_string(want);
-    });
+    }, "Failed to parse input sequence");
     // HashSet<Vec<u64>> de-duplication on encodings, first occurrence wins (src/cluster.rs:24,46-48)
     const size_t n_rec = in.n_ok;
     std::vector<uint8_t> first(n_rec, 0);
@@ -512,6 +541,7 @@ extern "C" int smafa_count_files(const char *const *paths, size_t n_paths, int o
       } catch (const Panic &e) {
         throw IoError(e.what());  // count() propagates parse errors with `?`
       }
+      if (!fx.parse_error.empty()) throw IoError(fx.parse_error);  // `let record = record?;` (src/lib.rs:385)
       size_t bases = 0;
       const std::vector<Record> &recs = fx.recs;
       for (const Record &r : recs) bases += r.seq.size();

@@ -1,7 +1,8 @@
 // `smafa` command line of the B200 drop-in.  Same subcommands and flags as the reference binary
-// (src/main.rs:64-116); additive flags: --device N, --kernel {auto,popc,mma}, --protein (amino-acid windows,
-// an extension: the reference only knows nucleotides).
+// (src/main.rs:64-116); additive flags: --device N / --devices a,b,... (query: the db is row-sharded over the listed
+// GPUs), --kernel {auto,popc,mma}, --protein (amino-acid windows, an extension: the reference only knows nucleotides).
 // Exit codes follow Rust: 0 ok, 101 for a reference panic, 1 for an Err from main, 2 usage.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,7 +19,7 @@ static int usage(const std::string &msg) {
           "error: %s\n\nUsage: smafa [-v|-q] <COMMAND>\n\nCommands:\n"
           "  makedb   Generate a searchable database            -i <FILE> -d <FILE>\n"
           "  query    Search a database                         -d <FILE> -q <FILE> [--max-divergence <INT>]\n"
-          "           [--max-num-hits <INT>] [--limit-per-sequence <INT>] [--device <INT>] [--kernel auto|popc|mma]\n"
+          "           [--max-num-hits <INT>] [--limit-per-sequence <INT>] [--device <INT> | --devices <INT,INT,...>] [--kernel auto|popc|mma]\n"
           "  cluster  Cluster sequences by similarity           -i <FILE> -d <INT> [--device <INT>] [--kernel ..]\n"
           "  (makedb/query/cluster: --protein treats the windows as amino acids -- an extension, not in the reference)\n"
           "  count    Print the number of reads/bases in a possibly gzipped FASTX file  -i <FILE>...\n",
@@ -89,6 +90,7 @@ int main(int argc_raw, char **argv_raw) {
   const char *input = nullptr, *database = nullptr, *query = nullptr;
   std::vector<const char *> inputs;
   int64_t m = -1, k = -1, r = -1, device = 0;
+  std::vector<int> devices;
   int kernel = SMAFA_KERNEL_AUTO;
   int alphabet = SMAFA_ALPHABET_NUCLEOTIDE;
   for (; i < argc; ++i) {
@@ -111,6 +113,18 @@ int main(int argc_raw, char **argv_raw) {
     else if (is_query && is(a, nullptr, "--limit-per-sequence")) { if (!need(&r)) return usage("invalid value for '--limit-per-sequence <INT>'"); }
     else if (!is_count && is(a, nullptr, "--protein")) alphabet = SMAFA_ALPHABET_PROTEIN;
     else if ((is_query || is_cluster) && is(a, nullptr, "--device")) { if (!need(&device)) return usage("invalid value for '--device <INT>'"); }
+    else if ((is_query || is_cluster) && is(a, nullptr, "--devices") && i + 1 < argc) {
+      // comma-separated GPU numbers: `query` row-shards the db over them; `cluster` uses the first
+      std::string list = argv[++i];
+      size_t p = 0;
+      while (p <= list.size()) {
+        const size_t c = std::min(list.find(',', p), list.size());
+        int64_t d = 0;
+        if (!parse_u32(list.substr(p, c - p).c_str(), &d) || d > 1023) return usage("invalid value for '--devices <INT,INT,...>'");
+        devices.push_back((int)d);
+        p = c + 1;
+      }
+    }
     else if ((is_query || is_cluster) && is(a, nullptr, "--kernel") && i + 1 < argc) {
       const std::string v = argv[++i];
       if (v == "auto") kernel = SMAFA_KERNEL_AUTO;
@@ -148,8 +162,9 @@ int main(int argc_raw, char **argv_raw) {
   // the context is created on a helper thread while the inputs are read and encoded (SMAFA_TIMING shows the wait)
   smafa_ctx *ctx = nullptr;
   int rc;
-  if (is_query) rc = smafa_query_file_on_device((int)device, kernel, alphabet, database, query, m, k, r, 1, &ctx);
-  else rc = smafa_cluster_file_on_device((int)device, kernel, alphabet, input, (uint32_t)m, 1, &ctx);
+  if (devices.empty()) devices.push_back((int)device);
+  if (is_query) rc = smafa_query_file_on_devices(devices.data(), (int)devices.size(), kernel, alphabet, database, query, m, k, r, 1, &ctx);
+  else rc = smafa_cluster_file_on_devices(devices.data(), (int)devices.size(), kernel, alphabet, input, (uint32_t)m, 1, &ctx);
   lap(is_query ? "query (all stages above)" : "cluster (all stages above)");
   int code = finish(rc, ctx);
   smafa_ctx_destroy(ctx);

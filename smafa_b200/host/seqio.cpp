@@ -289,15 +289,33 @@ FastxFile read_fastx(const std::string &path, bool io_error_on_open) {
     size_t p = 0;
     while (p < n) {
       if (b[p] == '\n' || b[p] == '\r') { ++p; continue; }
-      if (b[p] != '@') throw Panic("valid record: InvalidStart");
+      const size_t rec_no = f.recs.size() + 1;
+      if (b[p] != '@') {
+        f.parse_error = "ParseError { kind: InvalidStart, record: " + std::to_string(rec_no) + " }";
+        break;
+      }
       size_t ls[4], le[4];
-      for (int l = 0; l < 4; ++l) {
+      int lines = 0;
+      for (int l = 0; l < 4 && p < n; ++l, ++lines) {
         ls[l] = p;
         const void *nl = memchr(b + p, '\n', n - p);
         p = nl ? (size_t)((const uint8_t *)nl - b) : n;
         le[l] = p;
         if (le[l] > ls[l] && b[le[l] - 1] == '\r') --le[l];
         if (p < n) ++p;
+      }
+      // needletail rejects these (the reference then panics on the record): accept nothing it would not
+      if (lines < 4) {
+        f.parse_error = "ParseError { kind: UnexpectedEnd, record: " + std::to_string(rec_no) + " }";
+        break;
+      }
+      if (le[2] == ls[2] || b[ls[2]] != '+') {
+        f.parse_error = "ParseError { kind: InvalidSeparator, record: " + std::to_string(rec_no) + " }";
+        break;
+      }
+      if (le[3] - ls[3] != le[1] - ls[1]) {
+        f.parse_error = "ParseError { kind: UnequalLengths, record: " + std::to_string(rec_no) + " }";
+        break;
       }
       f.recs.push_back(Record{view(ls[0] + 1, le[0]), view(ls[1], le[1])});
     }
@@ -381,6 +399,8 @@ static void parse_body_sequential(Cursor &c, WindowDb &db) {
   for (uint64_t i = 0; i < db.n; ++i) {
     const uint64_t w = c.varint(10);
     if (i == 0) {
+      // every window costs at least 1 + W bytes: a count the file cannot hold is a truncated file, not an allocation
+      if (w > 512 || db.n > (c.n - c.p) / (w + 1) + 1) throw IoError("DeserializeUnexpectedEnd");
       db.W = (uint32_t)w;
       db.words.resize(db.n * db.W);
     } else if (w != db.W) {
@@ -489,6 +509,13 @@ WindowDb parse_db(const Bytes &bytes) {
   const uint8_t tag = c.b[c.p++];
   if (tag == 1) db.L = (uint32_t)c.varint(10);
   else if (tag != 0) throw IoError("DeserializeBadOption");
+  // `len` and the windows' word counts are separate fields of the file (src/lib.rs:54-60); makedb always writes them
+  // consistently (ceil(len / 12) words per window, src/lib.rs:32).  Everything downstream -- the device upload, the TSV
+  // decode, --limit-per-sequence -- derives the row stride from len, so a hand-made file that disagrees is refused
+  // here instead of being read with the wrong stride.
+  if (db.n > 0 && (db.L == 0 || db.W != words_for_len(db.L)))
+    throw IoError("db file is inconsistent: windows of " + std::to_string(db.W) + " words, window length " +
+                  (db.L ? std::to_string(db.L) : std::string("None")));
   return db;
 }
 

@@ -52,6 +52,11 @@ struct FastxFile {
   Bytes buf;                                      // the (decompressed) file: single-line sequences are views into it
   std::vector<std::deque<std::string>> arenas;    // re-assembled sequences (multi-line, stray CR), one arena per parser thread
   std::vector<Record> recs;
+  // Set when the records after recs.back() could not be parsed (FASTQ: no '+' line, quality and sequence of different
+  // lengths, a truncated last record).  needletail hands out records one by one, so the reference handles every
+  // record before the bad one and then panics on .expect(..) (src/lib.rs:149,234; src/cluster.rs:39) -- the callers
+  // here do the same with this text.
+  std::string parse_error;
   FastxFile() = default;
   FastxFile(FastxFile &&) = default;              // moving keeps every heap block, so the views stay valid
   FastxFile &operator=(FastxFile &&) = default;

@@ -1,7 +1,8 @@
-"""World-size-2 CPU (gloo) test of the multi-GPU plumbing in smafa_b200/dist.py: row-shard bounds,
-ragged candidate all-gather and the superset-merge argument.  No GPU: per-shard
-candidates come from the oracle, the merge is the oracle's finalize -- what is under test is the
-sharding / exchange / global-index logic the NCCL path shares."""
+"""World-size-2 CPU (gloo) test of the multi-GPU protocol: row-shard bounds, the fixed-capacity block
+all-gather with its overflow re-send and status propagation, and the sort-free merge -- as restated in
+tests/merge_model.py from smafa_b200/csrc/sharded.cu and merge.cu.  No GPU: per-shard answers come from the oracle, the
+blocks travel over gloo, the merged rows must equal the oracle's on the whole db.  (The CUDA merge itself is compared
+with the oracle by the -m gpu tests and by bench.py at every N.)"""
 import os
 import socket
 import subprocess
@@ -18,36 +19,49 @@ WORKER = textwrap.dedent("""
     import torch
     import torch.distributed as dist
     sys.path.insert(0, %(root)r)
-    from oracle import c_oracle, np_oracle
+    sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    from oracle import c_oracle
     from smafa_b200 import synth
-    from smafa_b200.dist import shard_bounds, exchange_candidates
+    from smafa_b200.dist import shard_bounds
+    import merge_model as mm
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     L = 60
-    db = synth.pack_symbols(synth.make_db(2001, L=L, seed=5))       # odd size: ragged shards
-    q = synth.pack_symbols(synth.make_queries(synth.make_db(2001, L=L, seed=5), 150, seed=6))
+    db_sym = synth.make_db(2001, L=L, seed=5)                        # odd size: ragged shards
+    db = synth.pack_symbols(db_sym)
+    q = synth.pack_symbols(synth.make_queries(db_sym, 150, seed=6))
     lo, hi = shard_bounds(db.shape[0], world, rank)
-    ok = True
-    for m, k in [(None, None), (5, None), (None, 10), (7, 10), (None, 3000), (0, None)]:
+    ok, regrown, failed_together = True, 0, False
+    for m, k in [(None, None), (5, None), (None, 10), (7, 10), (None, 3000), (0, None), (3, 1), ("fail", None)]:
+        status = 0
+        if m == "fail":                                              # rank 1's local part fails: everybody must learn it
+            m, status = 5, 11 if rank == 1 else 0
         local = c_oracle.query(db[lo:hi], L, q, L, m, k, None).astype(np.int64)
         local[:, 1] += lo                                            # global subject indices
-        if rank == 1 and m == 0:
-            local = local[:0]                                        # an empty block must survive the exchange
-            want_local_dropped = True
-        # capacity 64 forces the overflow retry for the big cases, the default path for the small ones
-        union, biggest = exchange_candidates(torch.from_numpy(local.astype(np.int32)), capacity=64 if k != 10 else 1 << 16)
-        ok = ok and biggest >= local.shape[0]
-        merged = np_oracle.finalize_candidates([tuple(int(x) for x in r) for r in union.numpy()], m, k)
-        if m == 0:
-            continue                                                 # rank 1 withheld rows on purpose
+        if status:
+            local = local[:0]
+        cap = 64                                                     # forces the overflow path for the big cases
+        while True:
+            block = torch.from_numpy(mm.make_block(local, cap, status).view(np.int64))
+            gathered = torch.empty(world * (2 + cap), dtype=torch.int64)
+            dist.all_gather_into_tensor(gathered, block)
+            rows, need, st, who = mm.merge_blocks(gathered.numpy().view(np.uint64).reshape(world, 2 + cap), cap, 1 if k in (None, 1) else k)
+            if need > cap and not st:
+                cap = mm.next_cap(need)                              # identical on every rank: all saw the same headers
+                regrown += 1
+                continue
+            break
+        if status or st:
+            failed_together = (st == 11 and who == 1)
+            continue
         want = c_oracle.query(db, L, q, L, m, k, None)
-        same = len(merged) == want.shape[0] and all(tuple(int(x) for x in w) == g for w, g in zip(want, merged))
-        ok = ok and same
-    t = torch.tensor([1 if ok else 0])
+        ok = ok and rows.shape == want.shape and bool((rows == want).all())
+    t = torch.tensor([1 if ok and failed_together else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"ok": bool(t.item()), "shards": [shard_bounds(db.shape[0], world, r) for r in range(world)]}))
+        print(json.dumps({"ok": bool(t.item()), "regrown": regrown,
+                          "shards": [shard_bounds(db.shape[0], world, r) for r in range(world)]}))
     dist.destroy_process_group()
 """)
 
@@ -63,7 +77,37 @@ def test_shard_bounds_cover_and_are_contiguous():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
-def test_two_rank_candidate_merge_matches_single_db(tmp_path):
+def test_merge_model_single_process():
+    """The merge of 1..5 shards (some empty, D < shards included) equals the oracle on the whole db in every mode."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import merge_model as mm
+    from oracle import c_oracle
+    from smafa_b200 import synth
+    from smafa_b200.dist import shard_bounds
+    c_oracle.build()
+    L = 33
+    for D, R in [(700, 1), (701, 3), (3, 5), (2000, 4)]:
+        db_sym = synth.make_db(D, L=L, seed=50 + D, family=8, max_subs=4)
+        db = synth.pack_symbols(db_sym)
+        q = synth.pack_symbols(synth.make_queries(db_sym, 90, seed=60 + D, max_subs=5))
+        for m, k in [(None, None), (4, None), (None, 7), (6, 7), (None, 5000), (2, 1)]:
+            blocks = []
+            for r in range(R):
+                lo, hi = shard_bounds(D, R, r)
+                if hi == lo:                                         # an empty shard of a non-empty db sends no rows
+                    blocks.append(mm.make_block(np.zeros((0, 3)), 1 << 16))
+                    continue
+                local = c_oracle.query(db[lo:hi], L, q, L, m, k, None).astype(np.int64)
+                local[:, 1] += lo
+                blocks.append(mm.make_block(local, 1 << 16))
+            rows, need, st, _ = mm.merge_blocks(np.stack(blocks), 1 << 16, 1 if k in (None, 1) else k)
+            want = c_oracle.query(db, L, q, L, m, k, None)
+            assert st == 0 and need <= 1 << 16
+            assert rows.shape == want.shape and (rows == want).all(), (D, R, m, k)
+
+
+def test_two_rank_block_exchange_matches_single_db(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
     with socket.socket() as s:
@@ -80,4 +124,5 @@ def test_two_rank_candidate_merge_matches_single_db(tmp_path):
     import json
     res = json.loads(outs[0][0].strip().splitlines()[-1])
     assert res["ok"], res
+    assert res["regrown"] >= 2                                       # the overflow path really ran
     assert res["shards"] == [[0, 1001], [1001, 2001]]

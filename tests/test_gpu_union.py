@@ -165,32 +165,40 @@ def test_union_append_parity(uctx):
 
 
 def test_degree_is_picked_per_scan():
-    """Library defaults.  Small batches follow the unrelated-window model (degree 3 from need >= 7L/8, 2 from 3L/4);
-    a batch large enough to be sampled gets what the sample says: windows with a skewed base composition (70 % A)
-    match a union row far too often for the union filter to pay (2 windows: 69 % of the positions, 3.7 sigma below
-    need = 55), so such a batch stays on single-window operands at a bound where uniform windows would get degree 3."""
+    """Library defaults.  Small batches follow the unrelated-window model (a row of u windows passes when
+    Binomial(L, 1 - (3/4)^u) >= need: degree 3 while need >= 47 of 60, degree 2 while need >= 39); a batch large enough
+    to be sampled gets what the sample says (cost model calibrated in profiles/r02_union_calib.log): windows with a
+    skewed base composition match a union row far more often -- at --max-divergence 5 a db with 85 % A stays on
+    single-window operands, one with 70 % A gets degree 2, uniform windows get degree 3."""
     L = 60
     c = smafa_b200.Context(0, "mma")
     try:
         db_sym = synth.make_db(2000, L=L, seed=51)
         db = synth.pack_symbols(db_sym)
         q = synth.pack_symbols(synth.make_queries(db_sym, 200, seed=52))
-        for m, k_want in [(5, 256 // 3), (7, 256 // 3), (8, 128), (15, 128), (16, 192), (40, 192)]:
-            check(c, db, q, L, m, 10)
+        for m, k_want in [(5, 256 // 3), (13, 256 // 3), (14, 128), (21, 128), (22, 192), (40, 192)]:
+            st = check(c, db, q, L, m, 10)
             assert c.last_mma_k == k_want, (m, c.last_mma_k)
+            assert st["union_degree"] == {256 // 3: 3, 128: 2, 192: 1}[k_want]
         rng = np.random.default_rng(61)
-        skew = rng.choice(4, size=(70_000, L), p=[0.7, 0.1, 0.1, 0.1]).astype(np.uint8)
-        qs = synth._mutate(rng, skew[rng.integers(0, len(skew), size=32_000)], 4, 0.01)        # 2.2e9 pairs: sampled
-        dbc, qc = synth.pack_symbols(skew), synth.pack_symbols(qs)
-        d = c.upload(dbc, L)
-        got = c.query(d, qc, L, max_divergence=5, max_num_hits=3)
-        assert c.last_mma_k == 192
-        uni = synth.pack_symbols(rng.integers(0, 4, size=(70_000, L), dtype=np.uint8))          # uniform bases: degree 3
-        d2 = c.upload(uni, L)
-        c.query(d2, qc, L, max_divergence=5, max_num_hits=3)
-        assert c.last_mma_k == 256 // 3
-        d.close()
-        d2.close()
+
+        def skewed(pA):
+            r = (1 - pA) / 3
+            return rng.choice(4, size=(70_000, L), p=[pA, r, r, r]).astype(np.uint8)
+
+        got = dbc = qc = None
+        for pA, k_want in [(0.85, 192), (0.70, 128), (0.25, 256 // 3)]:
+            sym = skewed(pA)
+            qs = synth._mutate(rng, sym[rng.integers(0, len(sym), size=32_000)], 4, 0.01)        # 2.2e9 pairs: sampled
+            dbw, qw = synth.pack_symbols(sym), synth.pack_symbols(qs)
+            d = c.upload(dbw, L)
+            rows = c.query(d, qw, L, max_divergence=5, max_num_hits=3)
+            assert c.last_mma_k == k_want, (pA, c.last_mma_k)
+            rows2 = c.query(d, qw, L, max_divergence=5, max_num_hits=3)                            # the kept verdict: same degree, same rows
+            assert c.last_mma_k == k_want and rows.shape == rows2.shape and (rows == rows2).all()
+            d.close()
+            if pA == 0.85:
+                got, dbc, qc = rows, dbw, qw
         sub = np.arange(0, len(qc), 997)
         want = c_oracle.query(dbc, L, qc[sub], L, 5, 3, None)
         rows = got[np.isin(got[:, 0], sub)].copy()

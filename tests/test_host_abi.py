@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(api.lib_path())
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
-    assert smafa_b200.load_library().smafa_abi_version() == 3
+    assert smafa_b200.load_library().smafa_abi_version() == 4
 
 
 def test_makedb_bytes_match_reference_fixtures(kats, kat_dir, tmp_path):

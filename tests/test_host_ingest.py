@@ -9,6 +9,7 @@ import sys
 import numpy as np
 import pytest
 
+import smafa_b200
 from smafa_b200 import api, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,6 +67,62 @@ def test_malformed_db_errors_do_not_depend_on_thread_count(big_db):
         one, many = _load(d / name, 1), _load(d / name, 8)
         assert one == many, name
     assert "error" in _load(d / "truncated", 8)
+
+
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7f) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_inconsistent_hand_made_db_is_refused(tmp_path):
+    """`len` and the windows' word counts are separate fields of the file (src/lib.rs:54-60).  A hand-made db that
+    states a length its windows cannot hold (or none at all) must be refused at load -- the device upload, the TSV decode
+    and --limit-per-sequence all derive the row stride from `len` -- and a window count the file cannot hold is a
+    truncated file, not an allocation."""
+    def db_bytes(n_words, stated_len, n_windows=3):
+        body = b"".join(_varint(n_words) + b"".join(_varint(16) for _ in range(n_words)) for _ in range(n_windows))
+        tail = b"\x00" if stated_len is None else b"\x01" + _varint(stated_len)
+        return _varint(2) + _varint(n_windows) + body + tail
+    good = tmp_path / "good.db"
+    good.write_bytes(db_bytes(1, 1))
+    words, L = smafa_b200.load_db_file(good)
+    assert L == 1 and words.shape == (3, 1) and (words == 16).all()
+    for name, blob in {"len_too_long": db_bytes(1, 60), "len_too_short": db_bytes(5, 12), "len_none": db_bytes(1, None),
+                       "count_beyond_file": _varint(2) + _varint(1 << 40) + _varint(1) + _varint(16) + b"\x01\x01"}.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        with pytest.raises(smafa_b200.SmafaError) as e:
+            smafa_b200.load_db_file(p)
+        assert e.value.status == "SMAFA_E_IO", name
+        q = tmp_path / "q.fna"
+        q.write_text(">a\nA\n")
+        r = subprocess.run([api.CLI_PATH, "query", "-d", p, "-q", q], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout == "", (name, r.stderr)       # refused before any device work
+
+
+def test_malformed_fastq_is_rejected_like_needletail(tmp_path):
+    """needletail rejects a FASTQ record without a '+' line, with quality and sequence of different lengths, or cut off
+    before its fourth line; the reference then panics on that record (src/lib.rs:149,234; src/cluster.rs:39) -- after the
+    records before it -- and `count` returns the error (src/lib.rs:385, exit code 1).  Unpinned by reference fixtures:
+    the message text is ours, the exit codes and the position of the failure are the reference's."""
+    ok = "@r0\nACGT\n+\nIIII\n"
+    cases = {"no_plus": ok + "@r1\nACGT\nIIII\nIIII\n", "qual_len": ok + "@r1\nACGT\n+\nIII\n",
+             "truncated": ok + "@r1\nACGT\n+\n", "bad_start": ok + "r1\nACGT\n+\nIIII\n"}
+    for name, text in cases.items():
+        p = tmp_path / (name + ".fq")
+        p.write_text(text)
+        r = subprocess.run([api.CLI_PATH, "makedb", "-i", p, "-d", tmp_path / "x.db"], capture_output=True, text=True)
+        assert r.returncode == 101 and "valid record" in r.stderr, (name, r.stderr)
+        r = subprocess.run([api.CLI_PATH, "count", "-i", p], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout == "", (name, r.stderr)
+    good = tmp_path / "good.fq"
+    good.write_text(ok + "@r1\nTTGA\n+r1\nIIII")                        # '+' may repeat the id; no final newline
+    r = subprocess.run([api.CLI_PATH, "count", "-i", good], capture_output=True, text=True)
+    assert r.returncode == 0 and '"num_reads":2,"num_bases":8' in r.stdout
 
 
 def test_first_bad_record_wins_for_every_thread_count(tmp_path):
