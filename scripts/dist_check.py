@@ -36,7 +36,9 @@ def check(name, s, dbw, qw, m, k):
     global ok
     qp = torch.from_numpy(qw.view(np.int64)).pin_memory()
     got = s.query_host(qp, m, k)
+    retries = s.last_stats["retries"]
     got_dev = s.query_dev(qp.to(dev), m, k).cpu().numpy().view(np.uint32)
+    retries += s.last_stats["retries"]
     same = got.shape == got_dev.shape and bool((got == got_dev).all())
     digest = torch.tensor([int(got.astype(np.uint64).sum() % (1 << 62)), got.shape[0]], dtype=torch.int64, device=dev)
     lo_d, hi_d = digest.clone(), digest.clone()
@@ -46,7 +48,9 @@ def check(name, s, dbw, qw, m, k):
     if rank == 0:
         want = c_oracle.query(dbw, L, qw, L, m, k, None, threads=threads)
         same = same and got.shape == want.shape and bool((got == want).all())
-        report[name] = [same, int(got.shape[0]), s.last_stats["retries"]]
+        report[name] = [same, int(got.shape[0]), retries]
+        if not same:
+            print("MISMATCH:", name, got.shape, got_dev.shape, want.shape, file=sys.stderr, flush=True)
     ok = ok and same
 
 
@@ -87,5 +91,7 @@ t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"ok": bool(t.item()), "world": world, "cases": report}))
+    bad = [k for k, v in report.items() if not v[0]]
+    print("failed cases:", bad, "overflow retries:", report.get("overflow m=5"), file=sys.stderr, flush=True)
 dist.destroy_process_group()
 sys.exit(0 if t.item() else 1)
