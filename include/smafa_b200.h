@@ -130,6 +130,19 @@ int smafa_ctx_set_candidate_capacity(smafa_ctx *ctx, uint64_t rows);
  * the reference). */
 int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)] */, uint64_t D,
                     uint32_t L, uint64_t subject_offset, smafa_db **db);
+/* Similarity-grouped order of a db (csrc/api.cu group_order): perm_out[r] = index of the window to store at row r, such
+ * that near-copies are neighbours and groups start at multiples of 16 rows where possible -- the order in which one
+ * tcgen05 accumulator can filter up to 16 db windows at once ("union rows").  smafa_db_upload applies it by
+ * itself (SMAFA_DB_GROUP=0 switches that off); callers that shard a db over processes call this once on the WHOLE db,
+ * cut the grouped order into their shards and upload them with smafa_db_upload_mapped, so that every shard holds whole
+ * groups.  *n_clusters = 0 and the identity when the db has too little structure (or is small, protein, longer than
+ * 63).  Results never depend on the order: rows are reported under their subject numbers. */
+int smafa_group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint32_t *perm_out /* [D] */,
+                      uint64_t *n_clusters);
+/* Rows in a caller-chosen order with explicit subject numbers: row r is reported as subject subjects[r] (< D_total, the
+ * rows of the whole db this one is a part of).  grouped != 0 states that the order is a similarity-grouped one. */
+int smafa_db_upload_mapped(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)] */, uint64_t D, uint32_t L,
+                           const uint32_t *subjects /* [D] */, uint64_t D_total, int grouped, smafa_db **db);
 /* Appends rows (used by cluster: the centroid set grows, src/cluster.rs:69-74). */
 int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n);
 uint64_t smafa_db_size(const smafa_db *db);

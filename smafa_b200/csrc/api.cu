@@ -304,37 +304,107 @@ constexpr int RC_TOO_MANY_CENTROIDS = 2;  // internal (cluster_impl)
 static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t, uint32_t *centroid_of,
                         uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats, uint64_t max_centroids);
 
-// Similarity-grouped db order (experimental, SMAFA_DB_GROUP=1).  Union rows (scan_mma.cu) filter
-// several windows with one accumulator, and how many they can hold is set by how often the union of a row's windows
-// matches an unrelated query -- hardly more often than one window when the windows of a row are near-copies of each
-// other.  perm = the db's windows ordered by (their centroid in the library's own greedy clustering at L/4, subject):
-// families become runs of consecutive rows.  Everything on the device then works on the grouped order; candidates
-// are mapped back to subject numbers before finalize (launch_remap_subjects), so results do not change.
-// Leaves perm empty when the db has too little structure (more centroids than half its windows).
-static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm) {
+// Similarity-grouped db order (DESIGN.md section 3b "Grouped rows").  Union rows (scan_mma.cu) filter several windows
+// with one accumulator, and how many they can hold is set by how often the union of a row's windows matches an
+// unrelated query -- hardly more often than one window when the windows of a row are near-copies of each other.
+// SingleM-style dbs are highly redundant, so the db is stored on the device in an order that puts similar windows
+// next to each other: perm[row] = input index of the window stored at `row`.  Everything on the device then works on
+// that order; candidates are mapped back to subject numbers before finalize (launch_remap_subjects), so results do
+// not change.
+//   1. clusters = the library's own greedy clustering (src/cluster.rs semantics, cluster_impl) at 2L/5: far below
+//      the distance of unrelated windows (3L/4 +- a few), wide enough to keep a family of near-copies together;
+//   2. clusters are laid out so that they start at multiples of 16 rows where possible -- a cluster that straddles two
+//      16-wide operand rows makes both of them pass for its queries: clusters of >= 16 windows first, each followed
+//      by small clusters that fill the rest of its last row exactly, then the remaining small ones packed into rows
+//      (largest first, best fit).  Members keep their input order inside a cluster.
+// Leaves perm empty when the db has too little structure to gain from it (more clusters than half its windows).
+static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm, uint64_t *n_clusters) {
   perm.clear();
+  if (n_clusters) *n_clusters = 0;
   std::vector<uint32_t> cof(D);
   uint64_t nc = 0;
   const bool saved = ctx->db_group;
   ctx->db_group = false;  // the greedy's own dbs are plain
-  int rc = cluster_impl(ctx, enc, D, L, L / 4, cof.data(), &nc, nullptr, nullptr, D / 2);
+  uint32_t t_group = 2 * L / 5;
+  if (const char *e = getenv("SMAFA_DB_GROUP_T")) t_group = (uint32_t)atoi(e);
+  int rc = cluster_impl(ctx, enc, D, L, t_group, cof.data(), &nc, nullptr, nullptr, D / 2);
   ctx->db_group = saved;
+  if (getenv("SMAFA_UNION_DEBUG"))
+    fprintf(stderr, "[smafa group] %llu windows, threshold %u: %llu clusters (rc %d)\n", (unsigned long long)D, t_group, (unsigned long long)nc, rc);
   if (rc == RC_TOO_MANY_CENTROIDS) return SMAFA_OK;
   if (rc) return rc;
-  // counting sort by centroid (centroids in input order, members in input order behind their centroid)
-  std::vector<uint32_t> start(D + 1, 0);
-  for (uint64_t i = 0; i < D; ++i) start[cof[i] + 1]++;
-  for (uint64_t i = 0; i < D; ++i) start[i + 1] += start[i];
+  if (n_clusters) *n_clusters = nc;
+  // cluster number (founding order) of every window, cluster sizes
+  std::vector<uint32_t> cid(D), size;
+  size.reserve(nc);
+  for (uint64_t i = 0; i < D; ++i) {
+    if (cof[i] == i) { cid[i] = (uint32_t)size.size(); size.push_back(0); }
+    else cid[i] = cid[cof[i]];  // a centroid precedes its members
+    size[cid[i]]++;
+  }
+  // layout: order of the clusters
+  constexpr uint32_t ROW = 16;
+  std::vector<std::vector<uint32_t>> small(ROW);  // small[s] = clusters of size s < ROW, founding order (used from the back)
+  std::vector<uint32_t> order;
+  order.reserve(size.size());
+  for (uint32_t c = (uint32_t)size.size(); c-- > 0;)
+    if (size[c] < ROW) small[size[c]].push_back(c);
+  uint32_t pos = 0;  // fill of the current row
+  auto fill_row = [&]() {  // completes the current row with the largest small clusters that fit
+    while (pos != 0) {
+      uint32_t gap = ROW - pos, s = gap;
+      while (s > 0 && small[s].empty()) --s;
+      if (s == 0) break;
+      order.push_back(small[s].back());
+      small[s].pop_back();
+      pos = (pos + s) % ROW;
+    }
+  };
+  for (uint32_t c = 0; c < size.size(); ++c) {
+    if (size[c] < ROW) continue;
+    order.push_back(c);
+    pos = (pos + size[c]) % ROW;
+    fill_row();
+  }
+  for (;;) {  // the remaining small clusters: largest first, then best fit into the rest of the row
+    uint32_t s = ROW - 1;
+    while (s > 0 && small[s].empty()) --s;
+    if (s == 0) break;
+    order.push_back(small[s].back());
+    small[s].pop_back();
+    pos = (pos + s) % ROW;
+    fill_row();
+  }
+  std::vector<uint64_t> start(size.size() + 1, 0);
+  for (uint32_t c : order) start[c] = 0;
+  uint64_t at = 0;
+  for (uint32_t c : order) { start[c] = at; at += size[c]; }
   perm.resize(D);
-  for (uint64_t i = 0; i < D; ++i) perm[start[cof[i]]++] = (uint32_t)i;
+  for (uint64_t i = 0; i < D; ++i) perm[start[cid[i]]++] = (uint32_t)i;
   return SMAFA_OK;
 }
 
-extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset,
-                               smafa_db **out) {
-  if (!ctx || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: null argument");
-  *out = nullptr;
-  if (ctx->multi) return multi_db_upload(ctx, enc, D, L, subject_offset, out);
+extern "C" int smafa_group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint32_t *perm_out, uint64_t *n_clusters) {
+  if (!ctx || (D && (!enc || !perm_out)) || L == 0) return fail(ctx, SMAFA_E_INVALID, "smafa_group_order: bad argument");
+  if (ctx->multi) ctx = multi_first(ctx);
+  if (D >= (1ull << 32)) return fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
+  std::vector<uint32_t> perm;
+  int rc = SMAFA_OK;
+  uint64_t nc = 0;
+  if (ctx->alphabet == ALPHA_NUC && L <= 63 && D >= 65536) rc = group_order(ctx, enc, D, L, perm, &nc);
+  if (rc) return rc;
+  if (n_clusters) *n_clusters = perm.empty() ? 0 : nc;
+  if (perm.empty())
+    for (uint64_t i = 0; i < D; ++i) perm_out[i] = (uint32_t)i;
+  else
+    memcpy(perm_out, perm.data(), D * sizeof(uint32_t));
+  return SMAFA_OK;
+}
+
+// subjects != nullptr: row r is reported as subject subjects[r] (+ subject_offset); grouped: the caller states that the
+// rows are in similarity-grouped order (wide union rows are packed).  try_group: let the library find such an order.
+int db_upload_rows(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset, const uint32_t *subjects,
+                   bool grouped, bool try_group, smafa_db **out) {
   if (D > 0 && (!enc || L == 0)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: D > 0 needs enc and L > 0");
   if (L > MAX_WINDOW_LEN) return fail(ctx, SMAFA_E_UNSUPPORTED, "window length %u > %u", L, MAX_WINDOW_LEN);
   CU(cudaSetDevice(ctx->device));
@@ -350,24 +420,56 @@ extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, 
   cudaError_t e = cudaMalloc((void **)&db->invalid_flag, sizeof(int));
   if (e != cudaSuccess) { delete db; return fail(ctx, SMAFA_E_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(db->invalid_flag, 0, sizeof(int), ctx->stream);
-  std::vector<uint64_t> grouped;
-  if (ctx->db_group && db->alphabet == ALPHA_NUC && !db->generic_only && L <= 63 && D >= 65536) {
-    int rc = group_order(ctx, enc, D, L, db->perm_host);
+  std::vector<uint64_t> reordered;
+  const bool eligible = db->alphabet == ALPHA_NUC && !db->generic_only && L <= 63;
+  if (subjects) {
+    db->perm_host.assign(subjects, subjects + D);
+    db->grouped = grouped && eligible;
+  } else if (try_group && eligible && D >= 65536) {
+    int rc = group_order(ctx, enc, D, L, db->perm_host, nullptr);
     if (rc) { smafa_db_free(db); return rc; }
     if (!db->perm_host.empty()) {
-      grouped.resize(D * db->W);
-      for (uint64_t r = 0; r < D; ++r)
-        memcpy(grouped.data() + r * db->W, enc + (uint64_t)db->perm_host[r] * db->W, db->W * sizeof(uint64_t));
-      enc = grouped.data();
-      e = cudaMalloc((void **)&db->perm, D * sizeof(uint32_t));
-      if (e == cudaSuccess) e = cudaMemcpyAsync(db->perm, db->perm_host.data(), D * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { smafa_db_free(db); return fail(ctx, SMAFA_E_OOM, "grouped db order: %s", cudaGetErrorString(e)); }
+      reordered.resize(D * db->W);
+      const uint32_t W = db->W;
+      const uint32_t *pm = db->perm_host.data();
+      for (uint64_t r = 0; r < D; ++r) memcpy(reordered.data() + r * W, enc + (uint64_t)pm[r] * W, W * sizeof(uint64_t));
+      enc = reordered.data();
+      db->grouped = true;
     }
+  }
+  if (!db->perm_host.empty()) {
+    db->perm_cap = std::max<uint64_t>(D, 256);
+    e = cudaMalloc((void **)&db->perm, db->perm_cap * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db->perm, db->perm_host.data(), D * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { smafa_db_free(db); return fail(ctx, SMAFA_E_OOM, "db row -> subject table: %s", cudaGetErrorString(e)); }
   }
   int rc = db_add_rows(ctx, db, enc, D);
   if (rc) { smafa_db_free(db); return rc; }
   *out = db;
   return SMAFA_OK;
+}
+
+extern "C" int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset,
+                               smafa_db **out) {
+  if (!ctx || !out) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: null argument");
+  *out = nullptr;
+  if (ctx->multi) return multi_db_upload(ctx, enc, D, L, subject_offset, out);
+  return db_upload_rows(ctx, enc, D, L, subject_offset, nullptr, false, ctx->db_group, out);
+}
+
+// Rows in a caller-chosen order with explicit subject numbers (a shard of a db that was grouped as a whole).
+extern "C" int smafa_db_upload_mapped(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, const uint32_t *subjects,
+                                      uint64_t D_total, int grouped, smafa_db **out) {
+  if (!ctx || !out || (D && !subjects)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload_mapped: null argument");
+  *out = nullptr;
+  if (ctx->multi) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_upload_mapped: a multi-device context shards its dbs itself");
+  if (D > D_total || D_total >= (1ull << 32)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload_mapped: %llu rows of a db of %llu",
+                                                            (unsigned long long)D, (unsigned long long)D_total);
+  for (uint64_t r = 0; r < D; ++r)
+    if (subjects[r] >= D_total) return fail(ctx, SMAFA_E_INVALID, "smafa_db_upload_mapped: subject %u of row %llu is outside the db", subjects[r], (unsigned long long)r);
+  int rc = db_upload_rows(ctx, enc, D, L, 0, subjects, grouped != 0, false, out);
+  if (rc == SMAFA_OK) (*out)->global_rows = D_total;
+  return rc;
 }
 
 // A shard of a row-sharded db: rows [subject_offset, subject_offset + D) of a db of D_total rows.
@@ -386,8 +488,30 @@ extern "C" int smafa_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc
   if (!ctx || !db || (n && !enc)) return fail(ctx, SMAFA_E_INVALID, "smafa_db_append: null argument");
   if (ctx->multi) return multi_db_append(ctx, db, enc, n);
   if (db->global_rows) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_append: the db is one shard of a larger db");
-  if (db->perm != nullptr && n) return fail(ctx, SMAFA_E_UNSUPPORTED, "smafa_db_append: the db is stored in grouped order (SMAFA_DB_GROUP)");
+  return db_append_rows(ctx, db, enc, n, db->D);
+}
+
+// first_subject: subject number of the first new window when the db has a row -> subject table (a db stored in grouped
+// order: the new windows go behind it under the next subject numbers)
+int db_append_rows(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n, uint64_t first_subject) {
   CU(cudaSetDevice(ctx->device));
+  if (db->perm != nullptr && n) {
+    const uint64_t D = db->D;
+    if (D + n > db->perm_cap) {
+      const uint64_t ncap = std::max<uint64_t>(D + n, db->perm_cap * 2);
+      uint32_t *np = nullptr;
+      CU(cudaMalloc((void **)&np, ncap * sizeof(uint32_t)));
+      cudaError_t e = cudaMemcpyAsync(np, db->perm, D * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) { cudaFree(np); return fail(ctx, SMAFA_E_CUDA, "smafa_db_append: %s", cudaGetErrorString(e)); }
+      cudaFree(db->perm);
+      db->perm = np;
+      db->perm_cap = ncap;
+    }
+    db->perm_host.resize(D + n);
+    for (uint64_t i = 0; i < n; ++i) db->perm_host[D + i] = (uint32_t)(first_subject + i);
+    CU(cudaMemcpyAsync(db->perm + D, db->perm_host.data() + D, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
   return db_add_rows(ctx, db, enc, n);
 }
 
@@ -433,7 +557,7 @@ extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_
     cudaMemcpyAsync(out + q0 * D, dout, nq * D * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "smafa_distances: %s", cudaGetErrorString(e2));
-    if (rc == SMAFA_OK && !db->perm_host.empty()) {  // grouped db: column r of the device result is subject perm[r]
+    if (rc == SMAFA_OK && !db->perm_host.empty() && !db->global_rows) {  // grouped db: column r of the device result is subject perm[r]
       std::vector<uint16_t> row(D);
       for (uint64_t q = q0; q < q0 + nq; ++q) {
         memcpy(row.data(), out + q * D, D * sizeof(uint16_t));
@@ -571,7 +695,7 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
     db->pick_age++;
     return std::min(db->pick_degree, max_u);
   }
-  if (db->perm != nullptr && max_u > 3) {
+  if (db->grouped && max_u > 3) {
     // Grouped db (experimental): rows up to 16 windows wide; always sampled (such a db has >= 65536 windows).
     const uint32_t q_stride = (nq + 4095) / 4096;
     const uint32_t n_d = (uint32_t)std::min<uint64_t>(1024, db->D);
@@ -1128,7 +1252,9 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
       }
     }
     lap(3);
-    if (cent_input.size() > max_centroids) { rc = RC_TOO_MANY_CENTROIDS; break; }
+    // group_order: give up on a db without near-duplicates early (its greedy would be quadratic)
+    if (cent_input.size() > max_centroids ||
+        (max_centroids != UINT64_MAX && b0 + B >= 131072 && cent_input.size() * 10 > (b0 + B) * 6)) { rc = RC_TOO_MANY_CENTROIDS; break; }
     if (!new_words.empty()) rc = db_add_rows(ctx, cdb, new_words.data(), new_words.size() / W);
     lap(4);
     b0 += B;

@@ -101,8 +101,10 @@ struct smafa_db {
   uint8_t *onehot = nullptr;
   uint32_t mma_nsym = 3;      // encoding of `onehot` (mma_pick_encoding)
   uint64_t onehot_cap = 0;
-  uint32_t *perm = nullptr;      // grouped dbs only: device row -> subject number (nullptr: rows are in subject order)
+  uint32_t *perm = nullptr;      // device row -> subject number (nullptr: rows are in subject order); grouped and mapped dbs
+  uint64_t perm_cap = 0;
   std::vector<uint32_t> perm_host;
+  bool grouped = false;          // rows are in similarity-grouped order (api.cu group_order, or stated by the caller): wide union rows
   // union-row images, one per degree of UNION_DEGREES: [tiles of 128*u windows][128 rows * 4 PB bytes]; degrees above
   // 3 only for grouped dbs (perm != nullptr)
   uint8_t *union_img[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -141,6 +143,11 @@ typedef std::function<int(uint64_t, uint64_t, uint64_t)> BatchSink;
 int run_query_range(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_dev, uint64_t n, uint64_t q_base, const QueryPlan &plan,
                     cudaStream_t s, smafa_stats *st, const BatchOut &out, const BatchSink &sink);
 int smafa_fail(smafa_ctx *ctx, int code, const char *fmt, ...);
+// subjects != nullptr: row r is reported as subject subjects[r] (+ subject_offset); grouped: the rows are in similarity-
+// grouped order (wide union rows are packed); try_group: let the library find such an order (api.cu group_order)
+int db_upload_rows(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset, const uint32_t *subjects,
+                   bool grouped, bool try_group, smafa_db **out);
+int db_append_rows(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t n, uint64_t first_subject);
 int ensure_query_words(smafa_ctx *ctx, size_t words);  // ctx->q_ref
 
 // ---- sharded.cu: entry points api.cu forwards to for a multi-device context ----

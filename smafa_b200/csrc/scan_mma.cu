@@ -107,17 +107,9 @@ constexpr int MMA_LIST_CAP = 256;  // ring entries per epilogue warp (power of t
 __device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_shared_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
-__device__ __forceinline__ bool mma_verify(const ScanParams &sp, uint32_t q, uint32_t j, int &d, int &bnd) {
-  if (q >= sp.Q || j >= sp.d_end) return false;
-  d = ref_distance(sp.q_ref + (size_t)q * sp.W, sp.d_ref + (size_t)j * sp.W, sp.W, sp.alphabet);
-  bnd = __ldcg(sp.bound + q);
-  return d <= bnd;
-}
-
-// Warp-converged: verifies 32 (q, j) pairs at a time (lane-private pair, `have` = lane holds one).
-__device__ __forceinline__ void mma_verify_emit_warp(const ScanParams &sp, bool have, uint32_t q, uint32_t j, uint32_t lane) {
-  int d = 0, bnd = 0;
-  const bool ok = have && mma_verify(sp, q, j, d, bnd);
+// Records the candidates of a warp (lane-private (q, j, d); `ok` = this lane holds one that passed the exact check):
+// one global atomicAdd per call for all of them, then the per-query bound tightening.  Warp-converged.
+__device__ __forceinline__ void mma_emit_warp(const ScanParams &sp, bool ok, uint32_t q, uint32_t j, int d, int &bnd, uint32_t lane) {
   const uint32_t mask = __ballot_sync(0xffffffffu, ok);
   if (mask) {
     const int leader = __ffs(mask) - 1;
@@ -129,6 +121,51 @@ __device__ __forceinline__ void mma_verify_emit_warp(const ScanParams &sp, bool 
       if (slot < sp.cand_cap) sp.cand[slot] = make_key(q, (uint32_t)d, j);
       tighten_bound(sp, q, d, bnd);
     }
+  }
+}
+
+// Exact re-check of one operand ROW per lane (`have` = the lane holds a survivor (q, row)): the row's UPR windows
+// row * UPR .. row * UPR + UPR - 1 are consecutive in the reference words, the query words are loaded once, and the
+// windows are evaluated four at a time with all their loads in flight together -- verification is a chain of L2
+// round trips whose latency, not whose work, is the cost (a wide row of a grouped db sends 16 windows here at once).
+// Warp-converged: every lane runs the same number of steps.
+template <int UPR>
+__device__ __forceinline__ void mma_verify_rows_warp(const ScanParams &sp, bool have, uint32_t q, uint32_t row, uint32_t lane) {
+  constexpr int WMAX = 6;  // mma_supported: L <= 63
+  have = have && q < sp.Q;
+  uint64_t qw[WMAX];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) qw[w] = (have && (uint32_t)w < sp.W) ? __ldg(sp.q_ref + (size_t)q * sp.W + w) : 0;
+  int bnd = have ? __ldcg(sp.bound + q) : -1;
+  constexpr int STEP = UPR < 4 ? UPR : 4;
+#pragma unroll 1
+  for (int c = 0; c < UPR; c += STEP) {
+    int d[STEP];
+    bool valid[STEP];
+#pragma unroll
+    for (int k = 0; k < STEP; ++k) {
+      const uint32_t j = row * UPR + c + k;
+      valid[k] = have && j < sp.d_end;
+      const uint64_t *dw = sp.d_ref + (size_t)(valid[k] ? j : 0) * sp.W;
+      int acc = 0;
+      if (sp.alphabet == ALPHA_NUC) {
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w)
+          if ((uint32_t)w < sp.W) acc += __popcll(qw[w] ^ __ldg(dw + w));
+        acc >>= 1;
+      } else {
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w)
+          if ((uint32_t)w < sp.W) {
+            const uint64_t x = qw[w] ^ __ldg(dw + w);
+            acc += __popcll((x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4)) & 0x0084210842108421ull);
+          }
+      }
+      d[k] = acc;
+    }
+    if (c > 0 && have) bnd = min(bnd, __ldcg(sp.bound + q));  // other warps may have tightened it meanwhile
+#pragma unroll
+    for (int k = 0; k < STEP; ++k) mma_emit_warp(sp, valid[k] && d[k] <= bnd, q, row * UPR + c + k, d[k], bnd, lane);
   }
 }
 
@@ -410,7 +447,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         }
       }
       __syncwarp();
-      const uint32_t n = (__popc(m0) + __popc(m1)) * UPR;  // ring entries: one per (query, window)
+      const uint32_t n = __popc(m0) + __popc(m1);  // ring entries: one per (query, operand row); the verifier expands the row
       uint32_t incl, total;
       if ((hitmask & (hitmask - 1)) == 0) {  // one lane holds all the survivors (the common case): no scan
         total = __shfl_sync(0xffffffffu, n, __ffs(hitmask) - 1);
@@ -424,60 +461,37 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         }
         total = __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (total > (uint32_t)MMA_LIST_CAP) {
-        // a flood (bound admits > 1/4 of the chunk): verify straight from the masks, warp-wide per bit
+      // Survivors normally go to the ring.  They are verified right here instead -- straight from the masks, warp-wide
+      // per bit -- in a flood (the bound admits > 1/8 of the chunk: more survivors than the ring holds) and when the
+      // ring stays full for ~0.1 s (a verifier warp that is not being scheduled: time-slicing, a profiler replay).
+      // Either way the answer is the same; nothing here can hang or poison the context.
+      bool inline_verify = total > (uint32_t)MMA_LIST_CAP;
+      if (!inline_verify && tail + total - head_seen > (uint32_t)MMA_LIST_CAP) {  // ring full: wait for the verifier warp
+        const long long t0 = clock64();
+        do {
+          head_seen = ld_shared_volatile(ring_head + (warp - 2));
+          if (clock64() - t0 > 200000000ll) { inline_verify = true; break; }
+        } while (tail + total - head_seen > (uint32_t)MMA_LIST_CAP);
+        __threadfence_block();  // the slots were read before the head moved
+      }
+      if (inline_verify) {
 #pragma unroll 1
         for (int i = 0; i < 32; ++i) {
-          if constexpr (UPR <= 3) {
-#pragma unroll
-            for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
-              mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
-              if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
-            }
-          } else {  // wide rows (grouped dbs): a loop, not UPR inlined copies of the verification
-#pragma unroll 1
-            for (uint32_t u = 0; u < (uint32_t)UPR; ++u) {
-              mma_verify_emit_warp(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row * UPR + u, lane);
-              if constexpr (PACK16) mma_verify_emit_warp(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row * UPR + u, lane);
-            }
-          }
+          mma_verify_rows_warp<UPR>(sp, (m0 >> i) & 1u, qc + (PACK16 ? 2 * i : i), row, lane);
+          if constexpr (PACK16) mma_verify_rows_warp<UPR>(sp, (m1 >> i) & 1u, qc + 2 * i + 1, row, lane);
         }
       } else {
-        if (tail + total - head_seen > (uint32_t)MMA_LIST_CAP) {  // ring full: wait for the verifier warp
-          const long long t0 = clock64();
-          do {
-            head_seen = ld_shared_volatile(ring_head + (warp - 2));
-            if (clock64() - t0 > 8000000000ll) __trap();
-          } while (tail + total - head_seen > (uint32_t)MMA_LIST_CAP);
-          __threadfence_block();  // the slots were read before the head moved
-        }
         uint32_t off = tail + incl - n;
         while (m0) {
           const int i = __ffs(m0) - 1;
           m0 &= m0 - 1;
-          if constexpr (UPR <= 3) {
-#pragma unroll
-            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
-          } else {
-#pragma unroll 4
-            for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-              my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row * UPR + u);
-          }
+          my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + (PACK16 ? 2 * i : i), row);
         }
         if constexpr (PACK16) {
           while (m1) {
             const int i = __ffs(m1) - 1;
             m1 &= m1 - 1;
-            if constexpr (UPR <= 3) {
-#pragma unroll
-              for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-                my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
-            } else {
-#pragma unroll 4
-              for (uint32_t u = 0; u < (uint32_t)UPR; ++u)
-                my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row * UPR + u);
-            }
+            my_list[off++ & (MMA_LIST_CAP - 1)] = make_uint2(qc + 2 * i + 1, row);
           }
         }
         tail += total;
@@ -595,7 +609,8 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         __nanosleep(nap);
         continue;
       }
-      if (total < 32u && !all_done && waited < 16u) {  // give a partial batch ~10 us to fill up
+      // give a partial batch ~10 us to fill up (wide rows: a single entry is already UPR windows of work)
+      if (total < (UPR >= 4 ? 8u : 32u) && !all_done && waited < (UPR >= 4 ? 4u : 16u)) {
         ++waited;
         __nanosleep(512);
         continue;
@@ -619,7 +634,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         for (uint32_t r = 0; r < RPV; ++r)
           if (lane == r) st_shared_volatile(ring_head + first + r, head[r]);
       }
-      mma_verify_emit_warp(sp, lane < taken, e.x, e.y, lane);
+      mma_verify_rows_warp<UPR>(sp, lane < taken, e.x, e.y, lane);
     }
   }
 
@@ -821,7 +836,7 @@ static int mma_fail(smafa_ctx *ctx, int code, const char *what, cudaError_t e) {
 static uint32_t union_kb(const smafa_db *db) { return 4 * mma_pb(4, db->L); }
 static uint32_t union_max_degree(const smafa_ctx *ctx, const smafa_db *db) {
   if (db->alphabet != ALPHA_NUC || !mma_enc_ok(4, db->L)) return 1;
-  if (db->perm != nullptr && ctx->mma_union >= 3) return 16;  // grouped db: near-copies share a row, wide rows stay selective
+  if (db->grouped && ctx->mma_union >= 3) return 16;  // grouped db: near-copies share a row, wide rows stay selective
   return std::min<uint32_t>(ctx->mma_union, 3);
 }
 
@@ -960,8 +975,14 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
     // degree 3, 6.5 -> 6.16 at degree 2, whole parity suite green under it: profiles/r02_union_calib_stages4.log,
     // r02_pytest_gpu_stages4.log); SMAFA_MMA_UNION_STAGES4=0 keeps the two-and-two shape reachable
     static const bool stages4 = getenv("SMAFA_MMA_UNION_STAGES4") ? atoi(getenv("SMAFA_MMA_UNION_STAGES4")) != 0 : true;
-    if (stages4 && wide && upr <= 3) {
-      e = upr == 2 ? launch_mma<8, 4, 4, 8, true, 1, false, 2>(P, grid, s) : launch_mma<8, 4, 4, 8, true, 1, false, 3>(P, grid, s);
+    if (stages4 && wide) {
+      switch (upr) {
+        case 2: e = launch_mma<8, 4, 4, 8, true, 1, false, 2>(P, grid, s); break;
+        case 3: e = launch_mma<8, 4, 4, 8, true, 1, false, 3>(P, grid, s); break;
+        case 4: e = launch_mma<8, 4, 4, 8, true, 1, false, 4>(P, grid, s); break;
+        case 8: e = launch_mma<8, 4, 4, 8, true, 1, false, 8>(P, grid, s); break;
+        default: e = launch_mma<8, 4, 4, 8, true, 1, false, 16>(P, grid, s); break;
+      }
       if (e != cudaSuccess) return mma_fail(ctx, SMAFA_E_CUDA, "scan_mma_kernel launch", e);
       return 2;
     }

@@ -494,6 +494,7 @@ static void shard_range(uint64_t D, size_t n, size_t r, uint64_t *lo, uint64_t *
 
 int multi_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint64_t subject_offset, smafa_db **out) {
   SmafaMulti *mu = ctx->multi;
+  const size_t R = mu->dev.size();
   if (D > 0 && (!enc || L == 0)) return smafa_fail(ctx, SMAFA_E_INVALID, "smafa_db_upload: D > 0 needs enc and L > 0");
   if (subject_offset + D >= (1ull << 32)) return smafa_fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
   smafa_db *db = new smafa_db();
@@ -503,11 +504,27 @@ int multi_db_upload(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L,
   db->W = (L + 11) / 12;
   db->subject_offset = subject_offset;
   db->alphabet = ctx->alphabet;
-  db->shards.assign(mu->dev.size(), nullptr);
-  int rc = on_every_device(mu, [&](size_t r) {
+  db->shards.assign(R, nullptr);
+  // The db is grouped as a whole (api.cu group_order, on the first device) and the GROUPED order is cut into the
+  // shards, so that every device holds whole families of similar windows; rows keep their subject numbers through the
+  // shards' row -> subject tables, which is all the merge needs.
+  int rc = SMAFA_OK;
+  if (mu->dev[0]->db_group && D >= 65536) {
+    db->perm_host.resize(D);
+    uint64_t nc = 0;
+    rc = smafa_group_order(mu->dev[0], enc, D, L, db->perm_host.data(), &nc);
+    if (rc) { adopt_error(ctx, rc); multi_db_free(db); return rc; }
+    if (nc == 0) db->perm_host.clear();  // no structure: plain contiguous shards
+  }
+  const bool mapped = !db->perm_host.empty();
+  db->grouped = mapped;
+  rc = on_every_device(mu, [&](size_t r) {
     uint64_t lo, hi;
-    shard_range(D, mu->dev.size(), r, &lo, &hi);
-    return smafa_db_upload(mu->dev[r], enc ? enc + lo * db->W : nullptr, hi - lo, L, subject_offset + lo, &db->shards[r]);
+    shard_range(D, R, r, &lo, &hi);
+    if (!mapped) return db_upload_rows(mu->dev[r], enc ? enc + lo * db->W : nullptr, hi - lo, L, subject_offset + lo, nullptr, false, false, &db->shards[r]);
+    std::vector<uint64_t> rows((hi - lo) * db->W);
+    for (uint64_t i = lo; i < hi; ++i) memcpy(rows.data() + (i - lo) * db->W, enc + (uint64_t)db->perm_host[i] * db->W, db->W * sizeof(uint64_t));
+    return db_upload_rows(mu->dev[r], rows.data(), hi - lo, L, subject_offset, db->perm_host.data() + lo, true, false, &db->shards[r]);
   });
   if (rc) { adopt_error(ctx, rc); multi_db_free(db); return rc; }
   *out = db;
@@ -518,8 +535,10 @@ int multi_db_append(smafa_ctx *ctx, smafa_db *db, const uint64_t *enc, uint64_t 
   // rows keep their global order when they join the last shard
   SmafaMulti *mu = ctx->multi;
   if (db->subject_offset + db->D + n >= (1ull << 32)) return smafa_fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
-  int rc = smafa_db_append(mu->dev.back(), db->shards.back(), enc, n);
+  int rc = db_append_rows(mu->dev.back(), db->shards.back(), enc, n, db->D);
   if (rc) return adopt_error(ctx, rc);
+  if (!db->perm_host.empty())
+    for (uint64_t i = 0; i < n; ++i) db->perm_host.push_back((uint32_t)(db->D + i));
   db->D += n;
   return SMAFA_OK;
 }
@@ -541,8 +560,15 @@ int multi_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_enc, u
     std::vector<uint16_t> part(Q * sh->D);
     int c = smafa_distances(mu->dev[r], sh, q_enc, Q, q_len, part.data());
     if (c) return c;
-    const uint64_t lo = sh->subject_offset - db->subject_offset;
-    for (uint64_t q = 0; q < Q; ++q) memcpy(out + q * db->D + lo, part.data() + q * sh->D, sh->D * sizeof(uint16_t));
+    if (db->perm_host.empty()) {
+      const uint64_t lo = sh->subject_offset - db->subject_offset;
+      for (uint64_t q = 0; q < Q; ++q) memcpy(out + q * db->D + lo, part.data() + q * sh->D, sh->D * sizeof(uint16_t));
+    } else {  // grouped db: column j of shard r is the window with subject number perm_host[first row of r + j]
+      uint64_t first = 0;
+      for (size_t o = 0; o < r; ++o) first += db->shards[o]->D;
+      for (uint64_t q = 0; q < Q; ++q)
+        for (uint64_t j = 0; j < sh->D; ++j) out[q * db->D + db->perm_host[first + j]] = part[q * sh->D + j];
+    }
     return (int)SMAFA_OK;
   });
   return adopt_error(ctx, rc);
