@@ -90,9 +90,8 @@ def workload_name(a, n):
 
 def make_inputs(a, rank, n):
     """ONE db of n x db_per_gpu windows (the SURVEY 8d generator, one seed), queries drawn from the whole of it.
-    Returns (this rank's shard as words, query words, first global row of the shard, whole db as symbols)."""
+    Returns (whole db as words, query words, whole db as symbols)."""
     from smafa_b200 import synth
-    from smafa_b200.dist import shard_bounds
     D = a.db_per_gpu * n
     if a.alphabet == "protein":
         db_sym = synth.make_db_aa(D, L=L, seed=synth.SEED_PROTEIN)
@@ -102,8 +101,9 @@ def make_inputs(a, rank, n):
         db_sym = synth.make_db(D, L=L, seed=synth.SEED_DB)
         q_sym = synth.make_queries(db_sym, a.queries, seed=synth.SEED_QUERY)
         pack = synth.pack_symbols
-    lo, hi = shard_bounds(D, n, rank)
-    return pack(db_sym[lo:hi]), pack(q_sym), lo, db_sym
+    # N > 1: every rank hands the WHOLE db to ShardedSearcher, which groups it as a whole (smafa_group_order) and keeps
+    # this rank's range of the grouped order -- contiguous shards of the plain order when the db has no structure to group
+    return pack(db_sym), pack(q_sym), db_sym
 
 
 def pack_db(db_sym):
@@ -252,8 +252,7 @@ def run_reference(a):
     if rank != 0:
         return
     world = max(1, int(os.environ.get("WORLD_SIZE", str(a.gpus))), a.gpus)
-    _, q, _, db_sym = make_inputs(a, 0, world)
-    db = pack_db(db_sym)
+    db, q, _ = make_inputs(a, 0, world)
     mode_k = None if a.mode == "a" else 10
     times, cb = [], None
     per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(1, a.steps + a.warmup)))
@@ -300,14 +299,16 @@ def main():
         # library's communicator id; the per-step exchange is the library's own ncclAllGather (csrc/sharded.cu)
         dist.init_process_group("nccl", device_id=dev)
 
-    shard, q, shard_lo, db_sym = make_inputs(a, rank, world)
-    D_total = db_sym.shape[0]
-    if rank != 0 or a.no_cpu_baseline:
-        db_sym = None  # only rank 0 needs the whole db again (oracle check)
+    db_words, q, db_sym = make_inputs(a, rank, world)
+    D_total = db_words.shape[0]
+    del db_sym
     ctx = smafa_b200.Context(local_rank, a.kernel)
     ctx.set_alphabet(a.alphabet)
-    searcher = ShardedSearcher(ctx, shard, L, world_size=world, rank=rank, presharded=True, shard_offset=shard_lo,
-                               total_rows=D_total)
+    t_up = time.perf_counter()
+    searcher = ShardedSearcher(ctx, db_words, L, world_size=world, rank=rank)
+    t_up = time.perf_counter() - t_up
+    if rank != 0 or a.no_cpu_baseline:
+        db_words = None  # only rank 0 needs the whole db again (oracle check)
     mode_k = None if a.mode == "a" else 10
     q_pinned = torch.from_numpy(q.view(np.int64)).pin_memory()
     q_dev = q_pinned.to(dev)
@@ -389,7 +390,10 @@ def main():
             "config": {"workload": workload_name(a, world), "kernel": {1: "popc", 2: "mma", 0: "generic"}[st["kernel_used"]],
                        "l2": "flushed between timed steps (256 MiB write)", "hit_rows": int(n_rows),
                        "candidates_per_step": int(st["candidates"]), "parallelism": f"db-row-shard x{world}",
-                       "db": f"one {D_total}-window db (seed {0x5AFA0001:#x}), contiguous row shards, queries drawn from the whole db",
+                       "db": f"one {D_total}-window db (seed {0x5AFA0001:#x}), queries drawn from the whole db; stored on the device in "
+                             "similarity-grouped order (smafa_group_order), " + ("the grouped order cut into one contiguous range per GPU"
+                                                                                 if world > 1 else "one GPU"),
+                       "db_upload_s": round(t_up, 3), "union_degree": int(st.get("union_degree", 0)),
                        "rows_identical_on_all_ranks": same_everywhere,
                        # selection without a useful bound scans under a guessed bound first (csrc/guess.cu)
                        "guess_bound": int(st["guess_bound"]), "rescanned_queries": int(st["rescanned"])},
@@ -406,7 +410,7 @@ def main():
         if not a.no_cpu_baseline:
             # rank 0: the oracle on a bounded prefix of the same queries against the WHOLE db -- the timing is the CPU
             # baseline, the rows are the parity check of the sharded scan + exchange + merge at this N
-            cb, cpu_hits, n = cpu_baseline(pack_db(db_sym), q, a.cpu_seconds if world == 1 else min(a.cpu_seconds, 8.0), mode_k)
+            cb, cpu_hits, n = cpu_baseline(db_words, q, a.cpu_seconds if world == 1 else min(a.cpu_seconds, 8.0), mode_k)
             got = host_rows[host_rows[:, 0] < n]
             cb["matches_gpu_rows"] = bool(got.shape == cpu_hits.shape and (got == cpu_hits).all()) and same_everywhere
             cb["checked_queries"] = int(n)

@@ -117,6 +117,8 @@ def load_library():
     l.smafa_ctx_comm_free.argtypes = [vp]
     l.smafa_ctx_comm_free.restype = None
     l.smafa_db_upload_shard.argtypes = [vp, vp, u64, u32, u64, u64, C.POINTER(vp)]
+    l.smafa_db_upload_mapped.argtypes = [vp, vp, u64, u32, vp, u64, C.c_int, C.POINTER(vp)]
+    l.smafa_group_order.argtypes = [vp, vp, u64, u32, vp, C.POINTER(u64)]
     l.smafa_query_sharded.argtypes = [vp, vp, vp, u64, u32, i64, i64, C.POINTER(C.POINTER(Hit)), C.POINTER(u64),
                                       C.POINTER(Stats)]
     l.smafa_query_sharded_dev.argtypes = [vp, vp, vp, u64, u32, i64, i64, vp, u64, C.POINTER(u64), vp, C.POINTER(Stats)]
@@ -191,6 +193,21 @@ class Context:
 
     def upload_shard(self, enc, L, subject_offset, total_rows):
         return Db(self, enc, L, subject_offset, total_rows=total_rows)
+
+    def group_order(self, enc, L):
+        """Similarity-grouped order of a whole db (smafa_group_order): -> (perm uint32 [D], clusters found; 0 = the db
+        has too little structure and perm is the identity)."""
+        e = _words(enc)
+        perm = np.zeros(e.shape[0], dtype=np.uint32)
+        nc = C.c_uint64(0)
+        rc = self._l.smafa_group_order(self._h, e.ctypes.data, e.shape[0], int(L), perm.ctypes.data, C.byref(nc))
+        if rc:
+            _raise(rc, self._h)
+        return perm, nc.value
+
+    def upload_mapped(self, enc, L, subjects, total_rows, grouped=True):
+        """Rows in the caller's order under explicit subject numbers (a shard of a db that was grouped as a whole)."""
+        return Db(self, enc, L, 0, total_rows=total_rows, subjects=subjects, grouped=grouped)
 
     def query_sharded(self, db, q_enc, q_len, max_divergence=None, max_num_hits=None, return_stats=False):
         """Collective: every rank passes the same queries and receives the complete answer (uint32 [n, 3])."""
@@ -386,7 +403,7 @@ class Db:
     """GPU-resident window set (the reference's WindowSet, src/lib.rs:54-60), optionally one
     row-shard of it (subject_offset = first global row)."""
 
-    def __init__(self, ctx, enc, L, subject_offset=0, keep_host=True, total_rows=None):
+    def __init__(self, ctx, enc, L, subject_offset=0, keep_host=True, total_rows=None, subjects=None, grouped=True):
         self.ctx = ctx
         self._l = ctx._l
         e = _words(enc) if len(enc) else np.zeros((0, max((L + 11) // 12, 1)), dtype=np.uint64)
@@ -395,7 +412,12 @@ class Db:
         self.subject_offset = subject_offset
         self.host_words = e if keep_host else None
         self._h = C.c_void_p()
-        if total_rows is None:
+        if subjects is not None:
+            sub = np.ascontiguousarray(subjects, dtype=np.uint32)
+            assert sub.shape[0] == e.shape[0]
+            rc = self._l.smafa_db_upload_mapped(ctx.handle, e.ctypes.data if e.shape[0] else None, e.shape[0], int(L),
+                                                sub.ctypes.data, int(total_rows), 1 if grouped else 0, C.byref(self._h))
+        elif total_rows is None:
             rc = self._l.smafa_db_upload(ctx.handle, e.ctypes.data if e.shape[0] else None, e.shape[0], int(L),
                                          int(subject_offset), C.byref(self._h))
         else:  # one shard of a row-sharded db (one process per GPU)

@@ -114,6 +114,7 @@ extern "C" int smafa_ctx_create(smafa_ctx **out, int device, int kernel) {
   ctx->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("SMAFA_NO_PREPASS")) ctx->disable_prepass = e[0] == '1';
   if (const char *e = getenv("SMAFA_NO_GUESS")) ctx->disable_guess = e[0] == '1';
+  if (const char *e = getenv("SMAFA_NO_FAST_FINALIZE")) ctx->disable_fast = e[0] == '1';
   if (const char *e = getenv("SMAFA_FORCE_GUESS")) ctx->force_guess = atoi(e);
   if (const char *e = getenv("SMAFA_MMA_NSYM")) ctx->mma_nsym = (e[0] >= '2' && e[0] <= '5') ? (uint32_t)(e[0] - '0') : 3;
   // union rows are on unless an ablation pins the operand encoding (SMAFA_MMA_NSYM) or asks for single rows
@@ -169,6 +170,7 @@ extern "C" void smafa_ctx_destroy(smafa_ctx *ctx) {
   cudaFree(ctx->bound); cudaFree(ctx->hist); cudaFree(ctx->q_ref); cudaFree(ctx->q_planes);
   cudaFree(ctx->q_onehot);
   cudaFree(ctx->per_query); cudaFree(ctx->unfinished); cudaFree(ctx->q_ref2);
+  cudaFree(ctx->fz_counters); cudaFree(ctx->fz_starts); cudaFree(ctx->fz_info); cudaFree(ctx->fz_temp);
   cudaFree(ctx->d_scalars);
   cudaFreeHost(ctx->h_scalars);
   for (auto &ev : ctx->ev)
@@ -314,9 +316,8 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
 //   1. clusters = the library's own greedy clustering (src/cluster.rs semantics, cluster_impl) at 2L/5: far below
 //      the distance of unrelated windows (3L/4 +- a few), wide enough to keep a family of near-copies together;
 //   2. clusters are laid out so that they start at multiples of 16 rows where possible -- a cluster that straddles two
-//      16-wide operand rows makes both of them pass for its queries: clusters of >= 16 windows first, each followed
-//      by small clusters that fill the rest of its last row exactly, then the remaining small ones packed into rows
-//      (largest first, best fit).  Members keep their input order inside a cluster.
+//      16-wide operand rows makes both of them pass for its queries (see "layout" below).  Members keep their input
+//      order inside a cluster.
 // Leaves perm empty when the db has too little structure to gain from it (more clusters than half its windows).
 static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm, uint64_t *n_clusters) {
   perm.clear();
@@ -342,38 +343,29 @@ static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t
     else cid[i] = cid[cof[i]];  // a centroid precedes its members
     size[cid[i]]++;
   }
-  // layout: order of the clusters
+  // layout: order of the clusters.  A cluster of s windows ends s mod 16 rows past a row boundary when it starts on one,
+  // so what is packed are the remainders: clusters whose size is a multiple of 16 first (they keep the alignment), then
+  // chains of clusters whose remainders fill a row -- largest remainder first, then the best fit for what is left of
+  // the row -- so that a chain ends on a row boundary again.  Clusters that fit nowhere simply continue the chain.
   constexpr uint32_t ROW = 16;
-  std::vector<std::vector<uint32_t>> small(ROW);  // small[s] = clusters of size s < ROW, founding order (used from the back)
+  std::vector<std::vector<uint32_t>> rem(ROW);  // rem[r] = clusters with size % 16 == r, founding order (used from the back)
   std::vector<uint32_t> order;
   order.reserve(size.size());
-  for (uint32_t c = (uint32_t)size.size(); c-- > 0;)
-    if (size[c] < ROW) small[size[c]].push_back(c);
+  for (uint32_t c = (uint32_t)size.size(); c-- > 0;) rem[size[c] % ROW].push_back(c);
+  while (!rem[0].empty()) { order.push_back(rem[0].back()); rem[0].pop_back(); }
   uint32_t pos = 0;  // fill of the current row
-  auto fill_row = [&]() {  // completes the current row with the largest small clusters that fit
-    while (pos != 0) {
-      uint32_t gap = ROW - pos, s = gap;
-      while (s > 0 && small[s].empty()) --s;
-      if (s == 0) break;
-      order.push_back(small[s].back());
-      small[s].pop_back();
-      pos = (pos + s) % ROW;
+  for (;;) {
+    uint32_t r = ROW - 1;
+    if (pos != 0) {  // best fit for the rest of the row, else whatever is largest
+      r = ROW - pos;
+      while (r > 0 && rem[r].empty()) --r;
+      if (r == 0) r = ROW - 1;
     }
-  };
-  for (uint32_t c = 0; c < size.size(); ++c) {
-    if (size[c] < ROW) continue;
-    order.push_back(c);
-    pos = (pos + size[c]) % ROW;
-    fill_row();
-  }
-  for (;;) {  // the remaining small clusters: largest first, then best fit into the rest of the row
-    uint32_t s = ROW - 1;
-    while (s > 0 && small[s].empty()) --s;
-    if (s == 0) break;
-    order.push_back(small[s].back());
-    small[s].pop_back();
-    pos = (pos + s) % ROW;
-    fill_row();
+    while (r > 0 && rem[r].empty()) --r;
+    if (r == 0) break;
+    order.push_back(rem[r].back());
+    rem[r].pop_back();
+    pos = (pos + r) % ROW;
   }
   std::vector<uint64_t> start(size.size() + 1, 0);
   for (uint32_t c : order) start[c] = 0;
@@ -388,10 +380,11 @@ extern "C" int smafa_group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D
   if (!ctx || (D && (!enc || !perm_out)) || L == 0) return fail(ctx, SMAFA_E_INVALID, "smafa_group_order: bad argument");
   if (ctx->multi) ctx = multi_first(ctx);
   if (D >= (1ull << 32)) return fail(ctx, SMAFA_E_UNSUPPORTED, "db larger than 2^32-1 windows");
+  CU(cudaSetDevice(ctx->device));
   std::vector<uint32_t> perm;
   int rc = SMAFA_OK;
   uint64_t nc = 0;
-  if (ctx->alphabet == ALPHA_NUC && L <= 63 && D >= 65536) rc = group_order(ctx, enc, D, L, perm, &nc);
+  if (ctx->db_group && ctx->alphabet == ALPHA_NUC && L <= 63 && D >= 65536) rc = group_order(ctx, enc, D, L, perm, &nc);
   if (rc) return rc;
   if (n_clusters) *n_clusters = perm.empty() ? 0 : nc;
   if (perm.empty())
@@ -424,6 +417,7 @@ int db_upload_rows(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, 
   const bool eligible = db->alphabet == ALPHA_NUC && !db->generic_only && L <= 63;
   if (subjects) {
     db->perm_host.assign(subjects, subjects + D);
+    db->mapped = true;
     db->grouped = grouped && eligible;
   } else if (try_group && eligible && D >= 65536) {
     int rc = group_order(ctx, enc, D, L, db->perm_host, nullptr);
@@ -557,7 +551,7 @@ extern "C" int smafa_distances(smafa_ctx *ctx, const smafa_db *db, const uint64_
     cudaMemcpyAsync(out + q0 * D, dout, nq * D * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) rc = fail(ctx, SMAFA_E_CUDA, "smafa_distances: %s", cudaGetErrorString(e2));
-    if (rc == SMAFA_OK && !db->perm_host.empty() && !db->global_rows) {  // grouped db: column r of the device result is subject perm[r]
+    if (rc == SMAFA_OK && !db->perm_host.empty() && !db->mapped) {  // grouped db: column r of the device result is subject perm[r]
       std::vector<uint16_t> row(D);
       for (uint64_t q = q0; q < q0 + nq; ++q) {
         memcpy(row.data(), out + q * D, D * sizeof(uint16_t));
@@ -750,6 +744,101 @@ static uint32_t pick_union_degree(smafa_ctx *ctx, const smafa_db *db, const uint
   return best;
 }
 
+constexpr int RC_SLOW_PATH = 3;  // internal: the speculative batch did not hold, run it the ordinary way
+
+// The common batch, enqueued in one go: a tcgen05 scan under a useful starting bound, the sort-free selection of
+// finalize.cu ("buckets") and the output conversion, every kernel taking the candidate count from device memory --
+// then ONE read-back.  Nothing waits on the host between the kernels, so their launch latencies hide behind the scan.
+// The speculation -- candidates fit the workspace, no query holds more than BUCKET_MAX of them, the query words are
+// valid codes -- is checked on the device (fast_ok); when it fails nothing was written and the caller runs the batch
+// again through run_batch's ordinary path (sort-based selection, overflow handling, generic kernel).
+static int run_batch_fast(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
+                          const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st, const BatchOut &out) {
+  int rc;
+  const uint32_t hist_stride = (db->L + 1 + 3) / 4 * 4;
+  const size_t q1 = (size_t)Qb + 1;
+  if ((rc = ensure_buf(ctx, ctx->fz_counters, ctx->fz_counters_cap, 3 * q1))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->fz_starts, ctx->fz_starts_cap, 2 * q1))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->fz_info, ctx->fz_info_cap, (size_t)ctx->ws_cap))) return rc;
+  if ((rc = ensure_buf(ctx, ctx->fz_temp, ctx->fz_temp_cap, bucket_temp_bytes(Qb)))) return rc;
+  unsigned long long *cand_count = ctx->d_scalars + 0, *fast_ok = ctx->d_scalars + 6;
+  uint32_t *max_seg = reinterpret_cast<uint32_t *>(ctx->d_scalars + 5);
+  int *q_invalid = ctx->d_scratch_flag();
+  CU(cudaMemsetAsync(ctx->d_scalars, 0, 8 * sizeof(unsigned long long), s));
+  CU(cudaMemsetAsync(ctx->fz_counters, 0, 3 * q1 * sizeof(uint32_t), s));
+  int launches = 2;
+  cudaEventRecord(ctx->ev[0], s);
+  launch_init_bound(ctx->bound, Qb + 512, plan.bound0, s);
+  if (plan.mode == MODE_KTH) CU(cudaMemsetAsync(ctx->hist, 0, (size_t)Qb * hist_stride * sizeof(uint32_t), s));
+  if (db->alphabet == ALPHA_NUC) {
+    launch_check_codes(q_ref_dev, Qb, db->W, db->L, q_invalid, s);
+  } else {  // protein: validity comes with the class planes
+    if ((rc = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)Qb + 256) * db->row_words))) return rc;
+    launch_pack_planes(q_ref_dev, Qb, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
+  }
+  launches += 2;
+  ScanParams p{};
+  p.d_planes = db->planes;
+  p.d_ref = db->ref;
+  p.D = (uint32_t)db->D;
+  p.d_begin = 0;
+  p.d_end = (uint32_t)db->D;
+  p.W = db->W;
+  p.L = db->L;
+  p.alphabet = db->alphabet;
+  p.mode = plan.mode;
+  p.k = plan.k_scan;
+  p.bound = ctx->bound;
+  p.hist = ctx->hist;
+  p.hist_stride = hist_stride;
+  p.cand = ctx->cand;
+  p.cand_count = cand_count;
+  p.cand_cap = ctx->ws_cap;
+  p.per_query = ctx->fz_counters;
+  p.q_ref = q_ref_dev;
+  p.Q = Qb;
+  ctx->mma_bound0 = plan.bound0;
+  ctx->mma_union_pick = pick_union_degree(ctx, db, q_ref_dev, Qb, plan.bound0, s, &launches, &rc);
+  if (rc) return rc;
+  int l = mma_scan(ctx, db, p, s, nullptr);
+  if (l < 0) return l;
+  launches += l;
+  cudaEventRecord(ctx->ev[1], s);
+  // a rough upper bound of the candidate count sizes the grids (grid-stride kernels: any value is correct)
+  const uint64_t n_hint = std::min<uint64_t>(ctx->ws_cap, std::max<uint64_t>(4ull * Qb, ctx->cand_needed));
+  launches += launch_finalize_buckets(ctx->fw, ctx->cand, cand_count, ctx->ws_cap, max_seg, q_invalid, fast_ok, Qb, plan.k_fin,
+                                      ctx->fz_counters, ctx->fz_starts, ctx->fz_info, ctx->fz_temp, ctx->fz_temp_cap, db->perm, n_hint, s);
+  if (out.block)
+    launches += launch_block_append(ctx->fw.keys_sel, ctx->fw.n_selected, n_hint, q_base, db->subject_offset, out.block, out.block_cap, s);
+  else
+    launches += launch_keys_to_hits(ctx->fw, n_hint, q_base, db->subject_offset, out.hits ? out.hits : ctx->hits,
+                                    out.hits ? out.hits_cap : ctx->ws_cap, ctx->h_scalars + 1, s);
+  CU(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  const uint64_t n_cand = ctx->h_scalars[0];
+  if (st) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    st->scan_ms += ms;
+    st->kernel_launches += launches;
+  }
+  if (ctx->h_scalars[6] == 0) {  // nothing was written downstream (n_selected = 0): the ordinary path takes over
+    if (st) st->retries++;
+    ctx->fast_skip = 8;  // and keeps the next batches too: a workload that breaks the speculation once tends to do it again
+    return RC_SLOW_PATH;
+  }
+  ctx->cand_needed = n_cand;
+  if (st) {
+    st->kernel_used = SMAFA_KERNEL_MMA;
+    st->guess_bound = -1;
+    st->union_degree = ctx->mma_union_used;
+    st->candidates += n_cand;
+  }
+  *n_rows = out.block ? UINT64_MAX : ctx->h_scalars[1];
+  return SMAFA_OK;
+}
+
 // One batch (<= 2^20 queries, words already on the device).  Leaves *n_rows rows in ctx->hits.
 static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_dev, uint32_t Qb, uint32_t q_base,
                      const QueryPlan &plan, uint64_t *n_rows, cudaStream_t s, smafa_stats *st, const BatchOut &out = BatchOut()) {
@@ -808,18 +897,23 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
       return SMAFA_OK;
     }
     if (kern == SMAFA_KERNEL_MMA && nq < 64) kern = SMAFA_KERNEL_POPC;
-    if ((r = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)nq + 256) * db->row_words))) return r;
-    launch_pack_planes(q_dev, nq, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
+    const uint32_t n_tiles = (uint32_t)((db->D + 255) / 256);
+    const bool want_prepass = prepass && n_tiles >= 32;
+    if (kern == SMAFA_KERNEL_MMA && !want_prepass && db->alphabet == ALPHA_NUC) {
+      // the tcgen05 scan reads no bit planes: only the validity check of the query words is needed
+      launch_check_codes(q_dev, nq, db->W, db->L, q_invalid, s);
+      p.q_planes = nullptr;
+    } else {
+      if ((r = ensure_buf(ctx, ctx->q_planes, ctx->q_planes_cap, ((size_t)nq + 256) * db->row_words))) return r;
+      launch_pack_planes(q_dev, nq, db->W, db->L, db->row_words, db->alphabet, ctx->q_planes, q_invalid, s);
+      p.q_planes = ctx->q_planes;
+    }
     launches += 1;
-    p.q_planes = ctx->q_planes;
     // No useful starting bound (no or a loose --max-divergence): estimate one on a strided db
     // sample first, otherwise the first tiles of the scan would emit nearly every pair.
-    if (prepass) {
-      const uint32_t n_tiles = (uint32_t)((db->D + 255) / 256);
-      if (n_tiles >= 32) {
-        uint32_t sample_tiles = std::min<uint32_t>(std::max<uint32_t>(n_tiles / 32, 16), 224);
-        launches += launch_bound_prepass(p, std::max<uint32_t>(1, n_tiles / sample_tiles), s);
-      }
+    if (want_prepass) {
+      uint32_t sample_tiles = std::min<uint32_t>(std::max<uint32_t>(n_tiles / 32, 16), 224);
+      launches += launch_bound_prepass(p, std::max<uint32_t>(1, n_tiles / sample_tiles), s);
     }
     if (kern == SMAFA_KERNEL_MMA) {
       ctx->mma_bound0 = b0;
@@ -838,6 +932,12 @@ static int run_batch(smafa_ctx *ctx, const smafa_db *db, const uint64_t *q_ref_d
 
   const bool loose = plan.mode != MODE_FIXED && plan.bound0 * 3 > (int)db->L && !ctx->disable_prepass;
   const uint32_t need = plan.mode == MODE_KTH ? plan.k_scan : 1;  // rows that finish a query under a guessed bound
+  if (ctx->fast_skip > 0) {
+    ctx->fast_skip--;
+  } else if (kernel == SMAFA_KERNEL_MMA && Qb >= 64 && !loose && !ctx->disable_fast && ctx->mma_dump == nullptr && db->L <= 63) {
+    rc = run_batch_fast(ctx, db, q_ref_dev, Qb, q_base, plan, n_rows, s, st, out);
+    if (rc != RC_SLOW_PATH) return rc;
+  }
   uint64_t n_cand = 0;
   for (;;) {
     CU(cudaMemsetAsync(q_invalid, 0, sizeof(int), s));
@@ -1252,9 +1352,7 @@ static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_
       }
     }
     lap(3);
-    // group_order: give up on a db without near-duplicates early (its greedy would be quadratic)
-    if (cent_input.size() > max_centroids ||
-        (max_centroids != UINT64_MAX && b0 + B >= 131072 && cent_input.size() * 10 > (b0 + B) * 6)) { rc = RC_TOO_MANY_CENTROIDS; break; }
+    if (cent_input.size() > max_centroids) { rc = RC_TOO_MANY_CENTROIDS; break; }
     if (!new_words.empty()) rc = db_add_rows(ctx, cdb, new_words.data(), new_words.size() / W);
     lap(4);
     b0 += B;

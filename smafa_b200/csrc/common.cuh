@@ -75,6 +75,9 @@ struct ScanParams {
   uint64_t *cand;            // candidate keys
   unsigned long long *cand_count;
   uint64_t cand_cap;
+  // optional (tcgen05 scan only, else nullptr): candidates emitted per query, for the sort-free selection of
+  // finalize.cu (launch_finalize_buckets)
+  uint32_t *per_query;
 };
 
 // Tightens bound[q] after a candidate at distance d (<= bound) has been recorded.  `bound` is the

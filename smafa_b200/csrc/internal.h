@@ -42,7 +42,7 @@ struct smafa_ctx {
   uint32_t mma_nsym = 3;          // MMA operand encoding (scan_mma.cu): 3 = +-1 features (default); SMAFA_MMA_NSYM=2/4/5: ablations
   uint32_t mma_union = 1;         // largest union degree dbs get operand images for (1..3 windows per accumulator, scan_mma.cu); SMAFA_MMA_UNION
   double union_verify_ns = 0.03;  // cost of one verified window in pick_union_degree's model (profiles/r02_union_calib.log); SMAFA_UNION_VERIFY_NS
-  bool db_group = false;          // SMAFA_DB_GROUP=1 (experimental, off): large nucleotide dbs are stored in similarity-grouped order (api.cu group_order)
+  bool db_group = true;           // large nucleotide dbs are stored in similarity-grouped order (api.cu group_order); SMAFA_DB_GROUP=0: plain order
   int mma_union_force = 0;        // SMAFA_MMA_UNION_FORCE=u: every tcgen05 scan that starts at need >= L/2 uses degree u whatever the sample says (tests)
   uint32_t mma_union_pick = 1;    // degree of the next mma_scan (set per scan by run_batch)
   uint32_t mma_union_used = 0;    // degree the last mma_scan really ran with (1 when the db lacks the picked image)
@@ -69,12 +69,20 @@ struct smafa_ctx {
   uint64_t *q_ref = nullptr;      size_t q_ref_cap = 0;
   uint32_t *q_planes = nullptr;   size_t q_planes_cap = 0;
   uint8_t *q_onehot = nullptr;    size_t q_onehot_cap = 0;
+  // sort-free selection (finalize.cu launch_finalize_buckets)
+  uint32_t *fz_counters = nullptr; size_t fz_counters_cap = 0;  // [per_query | fill | kept], Q + 1 each
+  uint32_t *fz_starts = nullptr;   size_t fz_starts_cap = 0;    // [seg_start | kept_start], Q + 1 each
+  uint32_t *fz_info = nullptr;     size_t fz_info_cap = 0;      // per candidate: place in its bucket's order, keep flag
+  uint8_t *fz_temp = nullptr;      size_t fz_temp_cap = 0;      // CUB scan scratch
+  bool disable_fast = false;      // SMAFA_NO_FAST_FINALIZE=1: always the sort (ablation, tests)
+  uint32_t fast_skip = 0;         // batches that skip the speculative path after it failed (api.cu run_batch_fast)
   // optimistic first pass (guess.cu)
   uint32_t *per_query = nullptr;  size_t per_query_cap = 0;   // candidates per query after the first pass
   uint32_t *unfinished = nullptr; size_t unfinished_cap = 0;  // query numbers that need the second pass
   uint64_t *q_ref2 = nullptr;     size_t q_ref2_cap = 0;      // their words, compacted
   // scalars: [0] candidate count, [1] selected count, [2] scratch flag, [3] candidates kept after the first
-  // pass, [4] unfinished queries, [8..8+guess_bins) sampled distance histogram
+  // pass, [4] unfinished queries, [5] largest per-query candidate count, [6] fast_ok (finalize.cu buckets),
+  // [8..8+guess_bins) sampled distance histogram
   static constexpr int N_SCALARS = 8 + 72;
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;  // pinned mirror
@@ -104,6 +112,7 @@ struct smafa_db {
   uint32_t *perm = nullptr;      // device row -> subject number (nullptr: rows are in subject order); grouped and mapped dbs
   uint64_t perm_cap = 0;
   std::vector<uint32_t> perm_host;
+  bool mapped = false;           // the caller gave the subject numbers (smafa_db_upload_mapped, shards of a multi-device context)
   bool grouped = false;          // rows are in similarity-grouped order (api.cu group_order, or stated by the caller): wide union rows
   // union-row images, one per degree of UNION_DEGREES: [tiles of 128*u windows][128 rows * 4 PB bytes]; degrees above
   // 3 only for grouped dbs (perm != nullptr)

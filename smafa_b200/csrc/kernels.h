@@ -13,6 +13,8 @@ struct ScanParams;
 void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, uint32_t row_words, int alphabet,
                         uint32_t *planes, int *invalid, cudaStream_t s);
 void launch_init_bound(int *bound, uint32_t Q, int v, cudaStream_t s);
+// sets *invalid when a nucleotide word is not made of valid one-hot codes (what pack_planes checks, without the planes)
+void launch_check_codes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, int *invalid, cudaStream_t s);
 
 // scan_popc.cu -- return the number of kernels launched
 int launch_scan_popc(const ScanParams &p, bool early, uint32_t chunk, cudaStream_t s);
@@ -61,6 +63,14 @@ int launch_finalize(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uin
 int launch_finalize_select(FinalizeWorkspace &ws, const uint64_t *keys, uint64_t n, uint32_t n_queries, uint32_t k, cudaStream_t s);
 int launch_keys_to_hits(FinalizeWorkspace &ws, uint64_t n_max, uint32_t q_base, uint64_t subject_offset, smafa_hit *hits_out,
                         uint64_t hits_cap, unsigned long long *n_out_pinned, cudaStream_t s);
+
+// Sort-free selection for scans that counted their candidates per query (finalize.cu "buckets"): same result as
+// launch_finalize_select, no host-known row count; *fast_ok = 0 (and *ws.n_selected = 0) when the speculation fails.
+size_t bucket_temp_bytes(uint32_t Q);
+int launch_finalize_buckets(FinalizeWorkspace &ws, const uint64_t *cand, const unsigned long long *cand_count, uint64_t cap,
+                            const uint32_t *max_seg, const int *q_invalid, unsigned long long *fast_ok, uint32_t Q, uint32_t k,
+                            uint32_t *counters, uint32_t *starts, uint32_t *info, void *temp, size_t temp_bytes,
+                            const uint32_t *perm, uint64_t n_hint, cudaStream_t s);
 
 // merge.cu -- multi-GPU merge of per-shard blocks (see the file header)
 struct MergeWorkspace {

@@ -61,6 +61,27 @@ void launch_pack_planes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L,
   pack_planes_kernel<<<(n + 255) / 256, 256, 0, s>>>(ref, n, W, L, row_words, alphabet, planes, invalid);
 }
 
+// The validity half of pack_planes_kernel alone (nucleotide words): every used 5-bit group holds exactly one bit and
+// nothing sits above the window.  For scans that need no bit planes (tcgen05 kernel without a bound pre-pass).
+__global__ void check_codes_kernel(const uint64_t *__restrict__ ref, uint32_t n, uint32_t W, uint32_t L, int *__restrict__ invalid) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)n * W) return;
+  const uint32_t x = (uint32_t)(idx % W);
+  const uint64_t w = ref[idx];
+  const uint32_t used = (L >= 12 * (x + 1)) ? 12 : (L > 12 * x ? L - 12 * x : 0);
+  const uint64_t mask = used == 12 ? ((1ull << 60) - 1) : ((1ull << (5 * used)) - 1);
+  constexpr uint64_t LOW = 0x0084210842108421ull;  // bit 0 of each group
+  // per-group bit count, one 5-bit field per group (at most 5: no carry into the neighbour)
+  const uint64_t cnt = (w & LOW) + ((w >> 1) & LOW) + ((w >> 2) & LOW) + ((w >> 3) & LOW) + ((w >> 4) & LOW);
+  if ((w & ~mask) != 0 || cnt != (LOW & mask)) atomicOr(invalid, 1);
+}
+
+void launch_check_codes(const uint64_t *ref, uint32_t n, uint32_t W, uint32_t L, int *invalid, cudaStream_t s) {
+  const uint64_t t = (uint64_t)n * W;
+  if (t == 0) return;
+  check_codes_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(ref, n, W, L, invalid);
+}
+
 __global__ void init_bound_kernel(int *bound, uint32_t Q, int v) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Q) bound[i] = v;

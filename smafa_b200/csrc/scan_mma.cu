@@ -119,6 +119,7 @@ __device__ __forceinline__ void mma_emit_warp(const ScanParams &sp, bool ok, uin
     if (ok) {
       const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1));
       if (slot < sp.cand_cap) sp.cand[slot] = make_key(q, (uint32_t)d, j);
+      if (sp.per_query != nullptr) atomicAdd(sp.per_query + q, 1u);  // result unused: a fire-and-forget RED, no round trip
       tighten_bound(sp, q, d, bnd);
     }
   }
@@ -650,10 +651,16 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
 // encoding `enc` (see "operand encodings" above).  Rows >= n_valid are padding and can never pass the
 // sign filter.  Query rows (is_query) get their bias for the batch's initial need0 = L - bound0 and
 // their per-query constant in meta[].
+// ENC_C / IS_QUERY_C / ALPHA_C >= 0 fix the encoding, the side and the alphabet at compile time (the per-step query
+// operand and the nucleotide db images: the branches below fold away, ~3x faster than the generic instantiation).
+template <int ENC_C, int IS_QUERY_C, int ALPHA_C>
 __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end,
-                                    uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query,
-                                    int need0, int alphabet, int16_t *__restrict__ meta, uint8_t *__restrict__ out,
+                                    uint32_t W, uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc_rt, int is_query_rt,
+                                    int need0, int alphabet_rt, int16_t *__restrict__ meta, uint8_t *__restrict__ out,
                                     uint32_t upr) {
+  const uint32_t enc = ENC_C >= 0 ? (uint32_t)ENC_C : enc_rt;
+  const int is_query = IS_QUERY_C >= 0 ? IS_QUERY_C : is_query_rt;
+  const int alphabet = ALPHA_C >= 0 ? ALPHA_C : alphabet_rt;
   const bool aa_exact = enc == MMA_ENC_AA;
   const uint32_t chunks = KB / 16, PB = aa_exact ? MMA_AA_POS : KB / enc, gap = PB - L;
   // thread -> (row, k-chunk): eight consecutive threads take the eight rows of one core-matrix column, whose 16-byte
@@ -747,8 +754,14 @@ static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t 
                                 int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s, uint32_t upr = 1) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)((row_end - row_begin + 7) / 8) * 8 * (KB / 16);
-  pack_operand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB,
-                                                                enc, is_query, need0, alphabet, meta, out, upr);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+#define SMAFA_PACK_ARGS ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB, enc, is_query, need0, alphabet, meta, out, upr
+  if (alphabet == ALPHA_NUC && enc == 4 && is_query) pack_operand_kernel<4, 1, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
+  else if (alphabet == ALPHA_NUC && enc == 4) pack_operand_kernel<4, 0, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
+  else if (alphabet == ALPHA_NUC && enc == 3 && is_query) pack_operand_kernel<3, 1, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
+  else if (alphabet == ALPHA_NUC && enc == 3) pack_operand_kernel<3, 0, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
+  else pack_operand_kernel<-1, -1, -1><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
+#undef SMAFA_PACK_ARGS
 }
 
 // Peak probe: one thread per CTA issues back-to-back int8 MMAs (two alternating accumulators, ten

@@ -37,7 +37,7 @@ class ShardedSearcher:
     """Holds this rank's db shard on its GPU and answers replicated query batches (collective calls)."""
 
     def __init__(self, ctx, db_words, L, world_size=1, rank=0, group=None, hits_capacity=1 << 22, presharded=False,
-                 shard_offset=None, total_rows=None):
+                 shard_offset=None, total_rows=None, group_rows=True):
         self.ctx, self.L, self.group = ctx, L, group
         self.world_size, self.rank = world_size, rank
         self.W = (L + 11) // 12
@@ -52,9 +52,18 @@ class ShardedSearcher:
             shard = db_words[self.lo:hi]
             self.D_total = D
         self.device = torch.device("cuda", ctx.device)
+        self.clusters = 0
         if world_size > 1:
             init_comm(ctx, rank, world_size, group)
-            self.db = ctx.upload_shard(np.ascontiguousarray(shard), L, self.lo, self.D_total)
+            if not presharded and group_rows:
+                # The WHOLE db is grouped (every rank computes the same order on its own GPU: the greedy is exact and
+                # deterministic) and the grouped order is cut into the shards, so every rank holds whole families of similar
+                # windows -- what the wide union rows of the tcgen05 scan need.  Rows keep their subject numbers.
+                perm, self.clusters = ctx.group_order(db_words, L)
+            if self.clusters:
+                self.db = ctx.upload_mapped(np.ascontiguousarray(db_words[perm[self.lo:hi]]), L, perm[self.lo:hi], self.D_total)
+            else:
+                self.db = ctx.upload_shard(np.ascontiguousarray(shard), L, self.lo, self.D_total)
         else:
             self.db = ctx.upload(np.ascontiguousarray(shard), L, subject_offset=self.lo)
         self.hits = torch.empty((hits_capacity, 3), dtype=torch.int32, device=self.device)

@@ -171,7 +171,7 @@ def test_degree_is_picked_per_scan():
     skewed base composition match a union row far more often -- at --max-divergence 5 a db with 85 % A stays on
     single-window operands, one with 70 % A gets degree 2, uniform windows get degree 3."""
     L = 60
-    c = smafa_b200.Context(0, "mma")
+    c = _context(SMAFA_DB_GROUP=0)   # plain db order: degrees 1..3 (the grouped order has its own tests, test_gpu_grouped.py)
     try:
         db_sym = synth.make_db(2000, L=L, seed=51)
         db = synth.pack_symbols(db_sym)
