@@ -48,6 +48,8 @@ MMA_TRAFFIC = {
                            "db operand tiles + 19 MB query tiles, read once)"),
     85: (163.6e6 + 6.0e6, "ncu dram__bytes_read+write, profiles/r01_ncu_mma_v9_union3_summary.txt (algorithmic: 85 MB "
                           "union-row db image + 26 MB query tiles; the query tile is re-fetched per db chunk, mostly from L2)"),
+    16: (76.7e6 + 3.9e6, "constant from one ncu --set full capture, profiles/r02_ncu_mma_u16_summary.txt (algorithmic: 16 MB union-row db "
+                         "image of 16 windows per row + 26 MB query tiles + the reference words of verified windows)"),
 }
 
 

@@ -54,6 +54,7 @@ struct MmaParams {
   const uint8_t *a_tiles;  // [n_db_tiles][128 * KB]
   const uint8_t *b_tiles;  // [n_qtiles][256 * KB]
   uint32_t n_qtiles, n_chunks, tiles_per_chunk, n_db_tiles;
+  uint32_t qt_major;            // work-item order, see scan_mma_kernel ("work items")
   uint32_t desc_lbo, desc_sbo;  // smem descriptor strides in 16-byte units
   int need0;                    // initial L - bound (the bias stored in b_tiles)
   int32_t *dump;                // debug: raw accumulators of work item 0, tile 0 ([128][256]) or nullptr
@@ -263,33 +264,50 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
 
   const ScanParams &sp = P.sp;
   const uint32_t n_items = P.n_qtiles * P.n_chunks;
+  // Work items = (query tile, db chunk).  Chunk-major (qt_major = 0): CTA c takes items c, c + grid, ... of the order
+  // "all query tiles of chunk 0, then chunk 1, ..." -- the CTAs stream the same db chunk together, so a db image larger
+  // than L2 is read from DRAM once.  Query-tile-major (qt_major = 1, db images that fit L2: wide union rows): CTA c takes
+  // a contiguous range of the order "all chunks of query tile 0, then tile 1, ..." -- consecutive items share their query
+  // operand, which is then fetched once per tile instead of once per item, and with small chunks the CTAs finish within
+  // one chunk of each other.  The three roles walk the same item sequence.
+  const uint32_t item_begin = P.qt_major ? (uint32_t)((uint64_t)n_items * blockIdx.x / gridDim.x) : blockIdx.x;
+  const uint32_t my_items = P.qt_major ? (uint32_t)((uint64_t)n_items * (blockIdx.x + 1) / gridDim.x) - item_begin
+                                       : (n_items > blockIdx.x ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u);
+  auto item_of = [&](uint32_t it) { return P.qt_major ? item_begin + it : blockIdx.x + it * gridDim.x; };
+  auto qt_of = [&](uint32_t item) { return P.qt_major ? item / P.n_chunks : item % P.n_qtiles; };
+  auto chunk_of = [&](uint32_t item) { return P.qt_major ? item % P.n_chunks : item / P.n_qtiles; };
+  // does item `it` of this CTA need a query operand of its own (always, unless it continues the previous item's tile)
+  auto new_b_at = [&](uint32_t it) { return !P.qt_major || it == 0 || qt_of(item_of(it)) != qt_of(item_of(it - 1)); };
 
   if (warp == 0) {
     // ===== producer: bulk copies + bias refresh =====
-    uint32_t stage = 0, phase = 0, item_count = 0;
+    uint32_t stage = 0, phase = 0, b_ord = 0xffffffffu;  // b_ord = ordinal of the query operand in use (this CTA's n-th)
     int cur[8];
-    // Fetches the query operand of the work item with ordinal n (this CTA's n-th item) into buffer n % B_BUFS
-    // once the MMAs of the item that used the buffer before are done with it.
-    auto fetch_B = [&](uint32_t item, uint32_t n) {
+    int meta[8];  // per-query constant of this lane's queries (see MmaParams::q_meta)
+    // Fetches the query operand of tile qt as this CTA's n-th into buffer n % B_BUFS once the MMAs that used the
+    // buffer before are done with it.
+    auto fetch_B = [&](uint32_t qt, uint32_t n) {
       if (elect_one()) {
         const uint32_t b = n % B_BUFS, use = n / B_BUFS;
         if (use > 0) mbar_wait(B_EMPTY(b), (use - 1) & 1);
         mbar_expect_tx(B_FULL(b), B_BYTES);
-        bulk_g2s(smem_u32(sB0 + b * B_BYTES), P.b_tiles + (size_t)(item % P.n_qtiles) * B_BYTES, B_BYTES, B_FULL(b));
+        bulk_g2s(smem_u32(sB0 + b * B_BYTES), P.b_tiles + (size_t)qt * B_BYTES, B_BYTES, B_FULL(b));
       }
       __syncwarp();
     };
-    if (blockIdx.x < n_items) fetch_B(blockIdx.x, 0);
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
-      const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+    if (my_items) fetch_B(qt_of(item_of(0)), 0);
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint32_t item = item_of(it), chunk = chunk_of(item), qt = qt_of(item);
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      const uint32_t bb_ = item_count % B_BUFS;
+      const bool new_b = new_b_at(it);
+      if (new_b) ++b_ord;
+      const uint32_t bb_ = b_ord % B_BUFS;
       uint8_t *sB = sB0 + bb_ * B_BYTES;
-      const bool has_next = item + gridDim.x < n_items;
+      const bool has_next = it + 1 < my_items && new_b_at(it + 1);  // the next item needs an operand fetch
+      const uint32_t next_qt = it + 1 < my_items ? qt_of(item_of(it + 1)) : 0u;
       // with two buffers the next operand is requested once the ring has turned over (the item that
       // used that buffer is then certainly finished, so the wait inside fetch_B does not stall A loads)
       const uint32_t t_fetch = min(t_begin + (uint32_t)STAGES, t_end - 1);
-      int meta[8];  // per-query constant of this lane's queries (see MmaParams::q_meta)
       // bias value of a query at bound b: one-hot = need (stored negated), +-1 features = c_q
       auto bias_of = [&](int m, int b) -> int {
         const int need = max(0, min((int)sp.L - b, (int)sp.L));
@@ -297,11 +315,13 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
         else return max(0, min(need - m, 127));
       };
       const uint32_t k0 = HAD ? had_spare_k(0, PB, sp.L) : 0, k1 = HAD ? had_spare_k(1, PB, sp.L) : 0;
+      if (new_b) {  // a continued tile keeps the bias bytes (and cur[]) it has reached
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t q = qt * MMA_N + lane * 8 + i;
-        meta[i] = (NSYM != 5 && q < sp.Q) ? (int)P.q_meta[q] : 0;
-        cur[i] = bias_of(meta[i], (int)sp.L - P.need0);  // what pack_operand_kernel stored
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t q = qt * MMA_N + lane * 8 + i;
+          meta[i] = (NSYM != 5 && q < sp.Q) ? (int)P.q_meta[q] : 0;
+          cur[i] = bias_of(meta[i], (int)sp.L - P.need0);  // what pack_operand_kernel stored
+        }
       }
       // Bias refresh: each lane owns 8 consecutive queries of the tile.  The two 16-byte bound
       // loads are issued BEFORE the barrier wait so their L2 latency hides behind it (the bound
@@ -334,9 +354,9 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
       };
       int4 b0 = make_int4(0, 0, 0, 0), b1 = b0;
       if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
-      mbar_wait(B_FULL(bb_), (item_count / B_BUFS) & 1);
+      if (new_b) mbar_wait(B_FULL(bb_), (b_ord / B_BUFS) & 1);
       if (dyn) apply(b0, b1);
-      if (lane == 0) mbar_arrive(B_READY(bb_));
+      if (new_b && lane == 0) mbar_arrive(B_READY(bb_));
       for (uint32_t t = t_begin; t < t_end; ++t) {
         if (dyn) { b0 = __ldcg(bptr); b1 = __ldcg(bptr + 1); }
         if (elect_one()) {
@@ -345,11 +365,11 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
           bulk_g2s(smem_u32(sA + stage * A_BYTES), P.a_tiles + (size_t)t * A_BYTES, A_BYTES, FULL(stage));
         }
         __syncwarp();
-        if (B_BUFS == 2 && has_next && t == t_fetch) fetch_B(item + gridDim.x, item_count + 1);
+        if (B_BUFS == 2 && has_next && t == t_fetch) fetch_B(next_qt, b_ord + 1);
         if (dyn) apply(b0, b1);
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
-      if (B_BUFS == 1 && has_next) fetch_B(item + gridDim.x, item_count + 1);
+      if (B_BUFS == 1 && has_next) fetch_B(next_qt, b_ord + 1);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -357,17 +377,20 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
     // K-major A/B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t N_INST = SPLIT_N ? MMA_N / 2 : MMA_N;
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_INST >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
-    uint32_t stage = 0, phase = 0, tcount = 0, item_count = 0;
+    uint32_t stage = 0, phase = 0, tcount = 0, b_ord = 0xffffffffu;
     // descriptors: only the 14-bit start-address field changes (stage and k-step offsets, in 16-byte units)
     const uint64_t desc_hi = ((uint64_t)(P.desc_lbo & 0x3FFFu) << 16) | ((uint64_t)(P.desc_sbo & 0x3FFFu) << 32) | (1ull << 46);
     const uint64_t adesc_base = desc_hi | (uint64_t)((smem_u32(sA) >> 4) & 0x3FFFu);
     const uint64_t bdesc_base0 = desc_hi | (uint64_t)((smem_u32(sB0) >> 4) & 0x3FFFu);
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++item_count) {
-      const uint32_t chunk = item / P.n_qtiles;
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint32_t chunk = chunk_of(item_of(it));
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
-      const uint32_t bb_ = item_count % B_BUFS;
+      const bool new_b = new_b_at(it);
+      if (new_b) ++b_ord;
+      const bool last_of_b = it + 1 >= my_items || new_b_at(it + 1);  // the operand is free after this item
+      const uint32_t bb_ = b_ord % B_BUFS;
       const uint64_t bdesc_base = bdesc_base0 + (uint64_t)(bb_ * (B_BYTES >> 4));
-      mbar_wait(B_READY(bb_), (item_count / B_BUFS) & 1);
+      if (new_b) mbar_wait(B_READY(bb_), (b_ord / B_BUFS) & 1);
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, use = tcount >> 1;
         if constexpr (SPLIT_N) {
@@ -385,7 +408,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
               for (uint32_t ks = 1; ks < (uint32_t)KSTEPS; ++ks) tc_mma_i8<true>(d_tmem, ad + ks * 16, bd + ks * 16, idesc);
               if (h == 1) tc_commit(EMPTY(stage));
               tc_commit(TFULL(2 * buf + h));
-              if (h == 1 && t + 1 == t_end) tc_commit(B_EMPTY(bb_));
+              if (h == 1 && t + 1 == t_end && last_of_b) tc_commit(B_EMPTY(bb_));
             }
             __syncwarp();
           }
@@ -402,7 +425,7 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
               tc_mma_i8<true>(d_tmem, ad + ks * 16, bdesc_base + ks * 16, idesc);  // +256 bytes per k-step
             tc_commit(EMPTY(stage));  // smem stage reusable once these MMAs have read it
             tc_commit(TFULL(buf));    // accumulator ready for the epilogue
-            if (t + 1 == t_end) tc_commit(B_EMPTY(bb_));
+            if (t + 1 == t_end && last_of_b) tc_commit(B_EMPTY(bb_));
           }
           __syncwarp();
         }
@@ -504,8 +527,8 @@ __global__ void __launch_bounds__(mma_threads(EPI_WARPS), 1) scan_mma_kernel(con
       }
       __syncwarp();
     };
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const uint32_t chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint32_t item = item_of(it), chunk = chunk_of(item), qt = qt_of(item);
       const uint32_t t_begin = chunk * P.tiles_per_chunk, t_end = min(t_begin + P.tiles_per_chunk, P.n_db_tiles);
       const uint32_t qbase = qt * MMA_N + part * COLS_PER_WARP;
       for (uint32_t t = t_begin; t < t_end; ++t, ++tcount) {
@@ -700,6 +723,7 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
         make_uint4(oo[0], oo[1], oo[2], oo[3]);
     return;
   }
+  const uint32_t pb_shift = 31u - (uint32_t)__clz(PB);  // PB = 32 or 64 here (the protein one-hot returned above)
   const int alpha = enc == 2 ? 2 : 1, w5 = alpha + 4, T = (int)(enc * gap) - 3;
   const int over = max(0, nN - (T - 1));
   int qbase = 0, cq = 0;
@@ -710,7 +734,7 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
   uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
   for (uint32_t i = 0; i < 16; ++i) {
-    const uint32_t k = c * 16 + i, f = k / PB, p = k % PB;
+    const uint32_t k = c * 16 + i, f = k >> pb_shift, p = k & (PB - 1);
     int v = 0;
     if (p < L) {
       if (valid) {
@@ -970,6 +994,11 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   const uint64_t want_items = (uint64_t)ctx->num_sms * 16;
   while (tiles_per_chunk > 8 && (uint64_t)n_qtiles * ((P.n_db_tiles + tiles_per_chunk - 1) / tiles_per_chunk) < want_items)
     tiles_per_chunk /= 2;
+  // a db image that fits L2 with room to spare (wide union rows): query-tile-major order, small chunks (see the kernel)
+  static const int qt_major_env = getenv("SMAFA_MMA_QT_MAJOR") ? atoi(getenv("SMAFA_MMA_QT_MAJOR")) : -1;
+  const size_t image_bytes = (size_t)P.n_db_tiles * MMA_M * KB;
+  P.qt_major = qt_major_env >= 0 ? (uint32_t)(qt_major_env != 0 && use_union && image_bytes <= (48u << 20)) : 0u;
+  if (P.qt_major) tiles_per_chunk = 16;
   P.tiles_per_chunk = tiles_per_chunk;
   P.n_chunks = (P.n_db_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
   // K-major, no swizzle: LBO = distance between the two 16-byte k-chunks of one k-step (128 B),

@@ -37,7 +37,7 @@ def check_query(ctx, db, q, L, m, k, r=None, kernel="popc"):
         got, st = ctx.query(d, q, L, max_divergence=m, max_num_hits=k, limit_per_sequence=r, return_stats=True)
     finally:
         d.close()
-    want = c_oracle.query(db, L, q, L, m, k, r)
+    want = c_oracle.query(db, L, q, L, m, k, r, threads=os.cpu_count() or 1)
     assert got.shape == want.shape, (L, m, k, r, kernel, got.shape, want.shape)
     assert (got == want).all(), (L, m, k, r, kernel)
     return st
