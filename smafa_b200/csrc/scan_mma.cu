@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 #include "internal.h"
@@ -773,12 +774,75 @@ __global__ void pack_operand_kernel(const uint64_t *__restrict__ ref, uint32_t n
   *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// The per-step case of pack_operand_kernel written out: nucleotide QUERY rows of the 4-symbol one-hot operand (the B
+// side of every union-row scan).  A thread writes the 16 bytes of (row, k-chunk c): symbol f = c / (PB/16), positions
+// p0 .. p0+15 with p0 = (c % (PB/16)) * 16 -- the symbol's bit of position p is bit 5 (p % 12) + 4 - f of word p / 12, all
+// of it known per chunk at compile time (the switch below), so a byte costs a shift and a mask.  Only the threads of the
+// chunks that hold the bias byte (symbol A, position PB-1) and the per-query constant count the query's N's.
+template <uint32_t PB>
+__global__ void pack_query_onehot_kernel(const uint64_t *__restrict__ ref, uint32_t n_valid, uint32_t n_rows, uint32_t W, uint32_t L,
+                                         int need0, int16_t *__restrict__ meta, uint8_t *__restrict__ out) {
+  constexpr uint32_t KB = 4 * PB, CHUNKS = KB / 16, CPS = PB / 16;  // chunks per symbol
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = (uint32_t)(idx % (8 * CHUNKS));
+  const uint32_t row = (uint32_t)(idx / (8 * CHUNKS)) * 8 + (t & 7), c = t >> 3;
+  if (row >= n_rows) return;
+  const bool valid = row < n_valid;
+  uint64_t w[6] = {0, 0, 0, 0, 0, 0};
+  if (valid) {
+#pragma unroll
+    for (uint32_t x = 0; x < 6; ++x)
+      if (x < W) w[x] = __ldg(ref + (size_t)row * W + x);
+  }
+  const uint32_t f = c / CPS, part = c % CPS;
+  uint32_t o[4] = {0, 0, 0, 0};
+  auto fill = [&](auto P0) {
+    constexpr uint32_t p0 = decltype(P0)::value;
+#pragma unroll
+    for (uint32_t i = 0; i < 16; ++i) {
+      constexpr uint32_t dummy = 0;
+      (void)dummy;
+      const uint32_t p = p0 + i;
+      if (p < 72) {  // six words hold 72 positions; p < L is applied below
+        const uint32_t bit = (uint32_t)(w[p / 12] >> (5 * (p % 12) + 4 - f)) & 1u;
+        o[i >> 2] |= (p < L ? bit : 0u) << (8 * (i & 3));
+      }
+    }
+  };
+  switch (part) {
+    case 0: fill(std::integral_constant<uint32_t, 0>()); break;
+    case 1: fill(std::integral_constant<uint32_t, 16>()); break;
+    case 2: fill(std::integral_constant<uint32_t, 32>()); break;
+    default: fill(std::integral_constant<uint32_t, 48>()); break;
+  }
+  const bool bias_chunk = f == 0 && part == CPS - 1, meta_chunk = c == 0;
+  if (bias_chunk || meta_chunk) {
+    int nN = 0;
+#pragma unroll
+    for (uint32_t x = 0; x < 6; ++x) nN += __popcll(w[x] & 0x0084210842108421ull);
+    if (bias_chunk) {  // byte 15 of the chunk = position PB - 1 of symbol A: the negated need (see the file header)
+      const int v = valid ? -max(0, min(need0 - nN, 127)) : -128;
+      o[3] = (o[3] & 0x00ffffffu) | (((uint32_t)v & 0xffu) << 24);
+    }
+    if (meta_chunk && meta != nullptr) meta[row] = (int16_t)(valid ? nN : 0);
+  }
+  const uint32_t tile = row / MMA_N, r = row % MMA_N;
+  *reinterpret_cast<uint4 *>(out + (size_t)tile * MMA_N * KB + tile_offset(r, c * 16, KB)) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 static void launch_pack_operand(const uint64_t *ref, uint32_t n_valid, uint32_t row_begin, uint32_t row_end, uint32_t W,
                                 uint32_t L, uint32_t rows_per_tile, uint32_t KB, uint32_t enc, int is_query, int need0,
                                 int alphabet, int16_t *meta, uint8_t *out, cudaStream_t s, uint32_t upr = 1) {
   if (row_end <= row_begin) return;
   const uint64_t n = (uint64_t)((row_end - row_begin + 7) / 8) * 8 * (KB / 16);
   const unsigned grid = (unsigned)((n + 255) / 256);
+  static const bool fast_query_pack = getenv("SMAFA_NO_FAST_PACK") == nullptr;
+  if (fast_query_pack && alphabet == ALPHA_NUC && enc == 4 && is_query && upr == 1 && row_begin == 0 && rows_per_tile == MMA_N &&
+      W <= 6 && (KB == 256 || KB == 128)) {
+    if (KB == 256) pack_query_onehot_kernel<64><<<grid, 256, 0, s>>>(ref, n_valid, row_end, W, L, need0, meta, out);
+    else pack_query_onehot_kernel<32><<<grid, 256, 0, s>>>(ref, n_valid, row_end, W, L, need0, meta, out);
+    return;
+  }
 #define SMAFA_PACK_ARGS ref, n_valid, row_begin, row_end, W, L, rows_per_tile, KB, enc, is_query, need0, alphabet, meta, out, upr
   if (alphabet == ALPHA_NUC && enc == 4 && is_query) pack_operand_kernel<4, 1, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
   else if (alphabet == ALPHA_NUC && enc == 4) pack_operand_kernel<4, 0, ALPHA_NUC><<<grid, 256, 0, s>>>(SMAFA_PACK_ARGS);
@@ -989,11 +1053,26 @@ int mma_scan(smafa_ctx *ctx, const smafa_db *db, ScanParams &p, cudaStream_t s, 
   P.b_tiles = ctx->q_onehot;
   P.n_qtiles = n_qtiles;
   P.n_db_tiles = (uint32_t)((db->D + MMA_M * upr - 1) / (MMA_M * upr));
-  // work items = query tiles x db chunks; aim at a few hundred items per SM-resident CTA for balance
-  uint32_t tiles_per_chunk = 128;
-  const uint64_t want_items = (uint64_t)ctx->num_sms * 16;
-  while (tiles_per_chunk > 8 && (uint64_t)n_qtiles * ((P.n_db_tiles + tiles_per_chunk - 1) / tiles_per_chunk) < want_items)
-    tiles_per_chunk /= 2;
+  // Work items = query tiles x db chunks, dealt to the CTAs round-robin (chunk-major).  The scan ends with its slowest
+  // CTA, so the chunk count is chosen to minimise  rounds x (tiles per chunk + the hand-over between two items), rounds =
+  // ceil(items / CTAs): 100 k x 1 M at degree 16 is 391 query tiles x 489 db tiles -- 8 chunks give 3128 items = 22
+  // rounds of 62 tiles (1364 + hand-overs), 3 chunks give 1173 items = 8 rounds of 163 (1304): the ncu capture of the
+  // 8-chunk schedule had the SMs active 94 % of the time (profiles/r02_ncu_mma_u16_summary.txt).  Chunks stay below
+  // 1024 tiles so that a chunk's tiles remain L2-resident while all CTAs stream it.
+  uint32_t tiles_per_chunk = P.n_db_tiles;
+  {
+    const uint64_t ctas = std::min<uint64_t>((uint64_t)ctx->num_sms, (uint64_t)n_qtiles * P.n_db_tiles);
+    const uint32_t handover = 6;  // tile times lost between two items of a CTA (query operand swap)
+    uint64_t best_cost = UINT64_MAX;
+    for (uint32_t n = 1; n <= 96 && n <= P.n_db_tiles; ++n) {
+      const uint32_t per = (P.n_db_tiles + n - 1) / n;
+      if (per > 1024 && n < 96 && n < P.n_db_tiles) continue;
+      const uint32_t n_eff = (P.n_db_tiles + per - 1) / per;  // chunks of `per` tiles that are really needed
+      const uint64_t rounds = ((uint64_t)n_qtiles * n_eff + ctas - 1) / ctas;
+      const uint64_t cost = rounds * (per + handover);
+      if (cost < best_cost) { best_cost = cost; tiles_per_chunk = per; }
+    }
+  }
   // a db image that fits L2 with room to spare (wide union rows): query-tile-major order, small chunks (see the kernel)
   static const int qt_major_env = getenv("SMAFA_MMA_QT_MAJOR") ? atoi(getenv("SMAFA_MMA_QT_MAJOR")) : -1;
   const size_t image_bytes = (size_t)P.n_db_tiles * MMA_M * KB;

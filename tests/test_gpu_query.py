@@ -377,13 +377,17 @@ def test_mma_survivor_rings_under_pressure(ctx):
 
 # ---- optimistic first pass under a guessed bound (csrc/guess.cu) -----------------------------------
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", KERNELS + ["mma-union2", "mma-union3"])
 @pytest.mark.parametrize("guess", [0, 2, 7, 25])
 def test_guessed_bound_pass_is_exact(guess, kernel, monkeypatch):
     """Unbounded selection scans the batch under a guessed bound first and re-scans only the queries that did not find
     their k windows within it.  SMAFA_FORCE_GUESS pins the guess (the sampled estimate only switches on for >= 2e9
-    comparisons), so every split between the two passes is exercised: nothing finished (0), some, all (25)."""
+    comparisons), so every split between the two passes is exercised: nothing finished (0), some, all (25).  The
+    mma-union variants force the first pass (and every scan that starts at need >= L/2) onto union rows of that degree."""
     monkeypatch.setenv("SMAFA_FORCE_GUESS", str(guess))
+    if kernel.startswith("mma-union"):
+        monkeypatch.setenv("SMAFA_MMA_UNION_FORCE", kernel[-1])
+        kernel = "mma"
     c = smafa_b200.Context(0, kernel)
     try:
         for L in (20, 60):
@@ -397,7 +401,7 @@ def test_guessed_bound_pass_is_exact(guess, kernel, monkeypatch):
             for m, k, r in [(None, None, None), (None, 1, None), (None, 2, None), (None, 10, None), (None, 10, 1),
                             (L - 1, 25, None), (None, 5999, None), (None, 7000, None), (3, 10, None)]:
                 got, st = c.query(d, q, L, max_divergence=m, max_num_hits=k, limit_per_sequence=r, return_stats=True)
-                want = c_oracle.query(db, L, q, L, m, k, r)
+                want = c_oracle.query(db, L, q, L, m, k, r, threads=os.cpu_count() or 1)
                 assert got.shape == want.shape and (got == want).all(), (L, m, k, r, guess)
                 rescanned.append((st["guess_bound"], st["rescanned"]))
             d.close()
