@@ -23,6 +23,7 @@ synth.write_fasta(f"{tmp}/q.fna", synth.to_ascii(q_sym))
 synth.write_fasta(f"{tmp}/qsub.fna", synth.to_ascii(q_sym[:SUB]))
 synth.write_fasta(f"{tmp}/qsubb.fna", synth.to_ascii(q_sym[:SUB_B]))
 env = dict(os.environ, SMAFA_TIMING="1")
+DEV = ["--devices", os.environ["E2E_DEVICES"]] if os.environ.get("E2E_DEVICES") else []   # row-shard the db over several GPUs
 
 
 def run(cmd, **kw):
@@ -39,12 +40,12 @@ print(f"host threads available: {os.cpu_count()}; D={D} Q={Q}")
 r, dt = run([api.CLI_PATH, "makedb", "-i", f"{tmp}/db.fna", "-d", f"{tmp}/db.smafadb"])
 print(f"smafa makedb: {dt:.3f} s wall\n{r.stderr.decode()}")
 for args in (["--max-divergence", "5"], ["--max-divergence", "5", "--max-num-hits", "10"]):
-    r, dt = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/q.fna", *args])
+    r, dt = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/q.fna", *DEV, *args])
     full = r.stdout
-    print(f"smafa query {' '.join(args)}: {dt:.3f} s wall, {full.count(10)} lines, {Q * D / dt:.3e} comparisons/s end to end "
+    print(f"smafa query {' '.join(DEV + args)}: {dt:.3f} s wall, {full.count(10)} lines, {Q * D / dt:.3e} comparisons/s end to end "
           f"(process start, CUDA init, file I/O included)\n{r.stderr.decode()}")
     sub, subf = (SUB_B, "qsubb.fna") if "--max-num-hits" in args else (SUB, "qsub.fna")
-    rs, dts = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/{subf}", *args])
+    rs, dts = run([api.CLI_PATH, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/{subf}", *DEV, *args])
     ro, dto = run([c_oracle.CLI, "query", "-d", f"{tmp}/db.smafadb", "-q", f"{tmp}/{subf}", *args])
     same = rs.stdout == ro.stdout
     head = b"".join(l + b"\n" for l in full.split(b"\n") if l and int(l.split(b"\t", 1)[0]) < sub)
