@@ -139,6 +139,10 @@ int smafa_db_upload(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)] */, u
  * 63).  Results never depend on the order: rows are reported under their subject numbers. */
 int smafa_group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint32_t *perm_out /* [D] */,
                       uint64_t *n_clusters);
+/* The layout step of smafa_group_order alone (host only, no GPU): from a clustering -- centroid_of[i] = the window that
+ * founded window i's cluster, itself for a founder, as smafa_cluster reports it -- to the row order: clusters contiguous,
+ * members in input order, clusters arranged so that they start on multiples of 16 rows where their sizes allow. */
+int smafa_group_layout(const uint32_t *centroid_of, uint64_t D, uint32_t *perm_out /* [D] */);
 /* Rows in a caller-chosen order with explicit subject numbers: row r is reported as subject subjects[r] (< D_total, the
  * rows of the whole db this one is a part of).  grouped != 0 states that the order is a similarity-grouped one. */
 int smafa_db_upload_mapped(smafa_ctx *ctx, const uint64_t *enc /* [D][ceil(L/12)] */, uint64_t D, uint32_t L,

@@ -306,38 +306,16 @@ constexpr int RC_TOO_MANY_CENTROIDS = 2;  // internal (cluster_impl)
 static int cluster_impl(smafa_ctx *ctx, const uint64_t *enc, uint64_t n, uint32_t L, uint32_t t, uint32_t *centroid_of,
                         uint64_t *n_centroids, uint64_t *n_comparisons, smafa_stats *stats, uint64_t max_centroids);
 
-// Similarity-grouped db order (DESIGN.md section 3b "Grouped rows").  Union rows (scan_mma.cu) filter several windows
-// with one accumulator, and how many they can hold is set by how often the union of a row's windows matches an
-// unrelated query -- hardly more often than one window when the windows of a row are near-copies of each other.
-// SingleM-style dbs are highly redundant, so the db is stored on the device in an order that puts similar windows
-// next to each other: perm[row] = input index of the window stored at `row`.  Everything on the device then works on
-// that order; candidates are mapped back to subject numbers before finalize (launch_remap_subjects), so results do
-// not change.
-//   1. clusters = the library's own greedy clustering (src/cluster.rs semantics, cluster_impl) at 2L/5: far below
-//      the distance of unrelated windows (3L/4 +- a few), wide enough to keep a family of near-copies together;
-//   2. clusters are laid out so that they start at multiples of 16 rows where possible -- a cluster that straddles two
-//      16-wide operand rows makes both of them pass for its queries (see "layout" below).  Members keep their input
-//      order inside a cluster.
-// Leaves perm empty when the db has too little structure to gain from it (more clusters than half its windows).
-static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm, uint64_t *n_clusters) {
-  perm.clear();
-  if (n_clusters) *n_clusters = 0;
-  std::vector<uint32_t> cof(D);
-  uint64_t nc = 0;
-  const bool saved = ctx->db_group;
-  ctx->db_group = false;  // the greedy's own dbs are plain
-  uint32_t t_group = 2 * L / 5;
-  if (const char *e = getenv("SMAFA_DB_GROUP_T")) t_group = (uint32_t)atoi(e);
-  int rc = cluster_impl(ctx, enc, D, L, t_group, cof.data(), &nc, nullptr, nullptr, D / 2);
-  ctx->db_group = saved;
-  if (getenv("SMAFA_UNION_DEBUG"))
-    fprintf(stderr, "[smafa group] %llu windows, threshold %u: %llu clusters (rc %d)\n", (unsigned long long)D, t_group, (unsigned long long)nc, rc);
-  if (rc == RC_TOO_MANY_CENTROIDS) return SMAFA_OK;
-  if (rc) return rc;
-  if (n_clusters) *n_clusters = nc;
+// The layout half of group_order as a pure host function (no GPU; tests/test_host_abi.py drives it): centroid_of[i] =
+// index of the window that founded window i's cluster (itself for a founder; founders precede their members, as in
+// smafa_cluster's output), perm_out[row] = window stored at `row`.
+extern "C" int smafa_group_layout(const uint32_t *centroid_of, uint64_t D, uint32_t *perm_out) {
+  if (D && (!centroid_of || !perm_out)) return SMAFA_E_INVALID;
+  const uint32_t *cof = centroid_of;
+  for (uint64_t i = 0; i < D; ++i)
+    if (cof[i] > i || cof[cof[i]] != cof[i]) return SMAFA_E_INVALID;  // a founder precedes its members and founded itself
   // cluster number (founding order) of every window, cluster sizes
   std::vector<uint32_t> cid(D), size;
-  size.reserve(nc);
   for (uint64_t i = 0; i < D; ++i) {
     if (cof[i] == i) { cid[i] = (uint32_t)size.size(); size.push_back(0); }
     else cid[i] = cid[cof[i]];  // a centroid precedes its members
@@ -371,9 +349,41 @@ static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t
   for (uint32_t c : order) start[c] = 0;
   uint64_t at = 0;
   for (uint32_t c : order) { start[c] = at; at += size[c]; }
-  perm.resize(D);
-  for (uint64_t i = 0; i < D; ++i) perm[start[cid[i]]++] = (uint32_t)i;
+  for (uint64_t i = 0; i < D; ++i) perm_out[start[cid[i]]++] = (uint32_t)i;
   return SMAFA_OK;
+}
+
+// Similarity-grouped db order (DESIGN.md section 3b "Grouped rows").  Union rows (scan_mma.cu) filter several windows
+// with one accumulator, and how many they can hold is set by how often the union of a row's windows matches an
+// unrelated query -- hardly more often than one window when the windows of a row are near-copies of each other.
+// SingleM-style dbs are highly redundant, so the db is stored on the device in an order that puts similar windows
+// next to each other: perm[row] = input index of the window stored at `row`.  Everything on the device then works on
+// that order; candidates are mapped back to subject numbers before finalize (launch_remap_subjects), so results do
+// not change.
+//   1. clusters = the library's own greedy clustering (src/cluster.rs semantics, cluster_impl) at 2L/5: far below
+//      the distance of unrelated windows (3L/4 +- a few), wide enough to keep a family of near-copies together;
+//   2. clusters are laid out so that they start at multiples of 16 rows where possible -- a cluster that straddles two
+//      16-wide operand rows makes both of them pass for its queries (see "layout" below).  Members keep their input
+//      order inside a cluster.
+// Leaves perm empty when the db has too little structure to gain from it (more clusters than half its windows).
+static int group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, std::vector<uint32_t> &perm, uint64_t *n_clusters) {
+  perm.clear();
+  if (n_clusters) *n_clusters = 0;
+  std::vector<uint32_t> cof(D);
+  uint64_t nc = 0;
+  const bool saved = ctx->db_group;
+  ctx->db_group = false;  // the greedy's own dbs are plain
+  uint32_t t_group = 2 * L / 5;
+  if (const char *e = getenv("SMAFA_DB_GROUP_T")) t_group = (uint32_t)atoi(e);
+  int rc = cluster_impl(ctx, enc, D, L, t_group, cof.data(), &nc, nullptr, nullptr, D / 2);
+  ctx->db_group = saved;
+  if (getenv("SMAFA_UNION_DEBUG"))
+    fprintf(stderr, "[smafa group] %llu windows, threshold %u: %llu clusters (rc %d)\n", (unsigned long long)D, t_group, (unsigned long long)nc, rc);
+  if (rc == RC_TOO_MANY_CENTROIDS) return SMAFA_OK;
+  if (rc) return rc;
+  if (n_clusters) *n_clusters = nc;
+  perm.resize(D);
+  return smafa_group_layout(cof.data(), D, perm.data());
 }
 
 extern "C" int smafa_group_order(smafa_ctx *ctx, const uint64_t *enc, uint64_t D, uint32_t L, uint32_t *perm_out, uint64_t *n_clusters) {

@@ -147,3 +147,45 @@ def test_cli_accepts_clap_value_syntax(kat_dir, tmp_path):
     r = cli("count", f"-i{fa}")
     assert r.returncode == 0 and '"num_reads":2' in r.stdout
     assert cli("makedb", "--input").returncode == 2
+
+
+def test_group_layout_keeps_clusters_together_and_row_aligned():
+    """smafa_group_layout (host half of smafa_group_order, csrc/api.cu): clusters stay contiguous, members keep their
+    input order, and clusters are arranged so that they straddle as few 16-wide operand rows as their sizes allow."""
+    import ctypes as C
+    lib = smafa_b200.load_library()
+    lib.smafa_group_layout.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(3)
+
+    def layout(sizes):
+        # windows of the clusters interleaved at random; the first window of a cluster is its founder
+        labels = rng.permutation(np.repeat(np.arange(len(sizes)), sizes))
+        first = {}
+        cof = np.zeros(len(labels), dtype=np.uint32)
+        for i, c in enumerate(labels):
+            first.setdefault(c, i)
+            cof[i] = first[c]
+        perm = np.zeros(len(labels), dtype=np.uint32)
+        assert lib.smafa_group_layout(cof.ctypes.data, len(labels), perm.ctypes.data) == 0
+        assert sorted(perm.tolist()) == list(range(len(labels)))
+        lab = labels[perm]
+        runs = 1 + int((np.diff(lab) != 0).sum())
+        assert runs == len(sizes)                                   # every cluster is one run of rows
+        for c in range(len(sizes)):                                 # members in input order
+            rows = perm[lab == c]
+            assert (np.diff(rows.astype(np.int64)) > 0).all()
+        # rows touched by each cluster vs the fewest its size allows
+        start = {}
+        for r, c in enumerate(lab):
+            start.setdefault(c, r)
+        extra = sum(((start[c] + s - 1) // 16 - start[c] // 16 + 1) - (s + 15) // 16 for c, s in enumerate(sizes))
+        return extra
+
+    assert layout([16] * 40 + [32] * 5 + [48]) == 0                 # multiples of 16: perfectly aligned
+    assert layout([16] * 100 + [17] * 3) <= 3                       # three odd clusters must not shift the hundred others
+    assert layout([15, 1, 14, 2, 13, 3, 8, 8, 16, 16, 31, 1]) == 0  # remainders that pair up to full rows
+    sizes = rng.integers(1, 40, size=400).tolist()
+    assert layout(sizes) <= 0.35 * len(sizes)                       # random sizes: far fewer straddles than clusters
+    bad = np.array([1, 1, 2], dtype=np.uint32)                      # window 0 claims a founder that comes after it
+    out = np.zeros(3, dtype=np.uint32)
+    assert lib.smafa_group_layout(bad.ctypes.data, 3, out.ctypes.data) != 0
