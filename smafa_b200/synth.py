@@ -22,9 +22,10 @@ def pack_symbols(sym):
     """uint8 [n, L] symbol indices -> uint64 [n, ceil(L/12)] in the reference bit layout."""
     n, L = sym.shape
     out = np.zeros((n, words_for_len(L)), dtype=np.uint64)
-    codes = _CODE[sym]
-    for p in range(L):
-        out[:, p // 12] |= codes[:, p] << np.uint64(5 * (p % 12))
+    for lo in range(0, n, 1 << 19):  # in slabs: the u64 code image of 10 M windows would be 4.8 GB at once
+        codes = _CODE[sym[lo:lo + (1 << 19)]]
+        for p in range(L):
+            out[lo:lo + (1 << 19), p // 12] |= codes[:, p] << np.uint64(5 * (p % 12))
     return out
 
 
@@ -109,9 +110,10 @@ def pack_symbols_aa(sym):
     holding the symbol NUMBER (index + 1) in the same 5-bit groups as the nucleotide layout."""
     n, L = sym.shape
     out = np.zeros((n, words_for_len(L)), dtype=np.uint64)
-    codes = sym.astype(np.uint64) + np.uint64(1)
-    for p in range(L):
-        out[:, p // 12] |= codes[:, p] << np.uint64(5 * (p % 12))
+    for lo in range(0, n, 1 << 19):
+        codes = sym[lo:lo + (1 << 19)].astype(np.uint64) + np.uint64(1)
+        for p in range(L):
+            out[lo:lo + (1 << 19), p // 12] |= codes[:, p] << np.uint64(5 * (p % 12))
     return out
 
 
