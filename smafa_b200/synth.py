@@ -58,7 +58,10 @@ def _mutate(rng, base, max_subs, noise):
         shift = rng.integers(1, 4, size=rows.size).astype(np.uint8)
         out[rows, pos] = (base[rows, pos] + shift) & 3
     if noise > 0:
-        out[rng.random(out.shape) < noise] = 4
+        # in row slabs: the same draws in the same order as one rng.random(out.shape), without its 8 bytes per symbol at once
+        for lo in range(0, n, 1 << 19):
+            part = out[lo:lo + (1 << 19)]
+            part[rng.random(part.shape) < noise] = 4
     return out
 
 
